@@ -1,0 +1,431 @@
+#!/usr/bin/env python
+"""bench.py -- BPR interactions/sec of the MF training hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--optimizer sgd|adam] [--adam-mode dense|touched] [--dim D] [--batch B]
+
+Workload (BASELINE.json configs[1], SURVEY.md section 8d "cfg 2"): MF-BPR, 1M users x 100k
+items, dim 128, batch 65536, SGD lr 0.05; 256 pre-built batches of synthetic
+(user,pos,neg) triples -- user, pos ~ Zipf(1.05) over a seeded permutation of ids,
+neg ~ Uniform -- tables N(0, 0.1^2).  A "step" is one batch through
+fwd+bwd+optimizer update (MFEngine.train_single_batch).
+
+Prints ONE JSON line (see the keys below).  `value` is device-timed with inputs
+resident in HBM (the train_an_epoch inner loop, one C call); `e2e` runs the public
+engine API with pinned HOST index buffers, H2D + D2H inside the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+N_USERS, N_ITEMS = 1_000_000, 100_000
+N_PREBUILT = 256
+SEED = 2020
+ZIPF_A = 1.05
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--optimizer", default="sgd", choices=["sgd", "adam", "rmsprop"])
+    ap.add_argument("--adam-mode", default="dense", choices=["dense", "touched"])
+    ap.add_argument("--dim", type=int, default=128)
+    ap.add_argument("--batch", type=int, default=65536)
+    ap.add_argument("--users", type=int, default=N_USERS)
+    ap.add_argument("--items", type=int, default=N_ITEMS)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-steps", type=int, default=0, help="timed CPU steps (0 = auto, ~10-30 s)")
+    return ap.parse_args()
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+# --------------------------------------------------------------------------- #
+# synthetic interaction stream
+# --------------------------------------------------------------------------- #
+def zipf_sampler(n, a, gen, device):
+    """Zipf(a) over a seeded permutation of [0, n): inverse-CDF sampling on `device`."""
+    ranks = torch.arange(1, n + 1, dtype=torch.float64, device=device)
+    cdf = torch.cumsum(ranks.pow(-a), 0)
+    cdf = (cdf / cdf[-1]).float()
+    perm = torch.randperm(n, generator=gen, device=device)
+
+    def draw(size):
+        r = torch.rand(size, generator=gen, device=device)
+        return perm[torch.searchsorted(cdf, r).clamp_(max=n - 1)]
+
+    return draw
+
+
+def make_batches(n_users, n_items, batch, n_batches, seed, device):
+    gen = torch.Generator(device=device)
+    gen.manual_seed(seed)
+    du = zipf_sampler(n_users, ZIPF_A, gen, device)
+    di = zipf_sampler(n_items, ZIPF_A, gen, device)
+    n = batch * n_batches
+    users, pos = du(n), di(n)
+    neg = torch.randint(0, n_items, (n,), generator=gen, device=device, dtype=torch.int64)
+    return users.contiguous(), pos.contiguous(), neg.contiguous()
+
+
+def config_dict(a, world):
+    return {
+        "workload": "configs[1]: MF BPR %dM users x %dk items, dim=%d, batch=%d, 1xB200 per rank"
+                    % (a.users // 1_000_000, a.items // 1000, a.dim, a.batch),
+        "n_users": a.users, "n_items": a.items, "dim": a.dim, "batch_per_gpu": a.batch,
+        "global_batch": a.batch * world, "optimizer": a.optimizer,
+        "optimizer_mode": ("exact (SGD touches only batch rows)" if a.optimizer == "sgd" else a.adam_mode),
+        "lr": 0.05, "index_distribution": "user,pos ~ Zipf(1.05) on permuted ids; neg ~ Uniform",
+        "prebuilt_batches": N_PREBUILT,
+        "l2_policy": "inputs larger than L2: 563 MB of tables, %d distinct batches cycled" % N_PREBUILT,
+        "parallelism": "dp%d" % world if world > 1 else "single",
+    }
+
+
+# --------------------------------------------------------------------------- #
+# clocks
+# --------------------------------------------------------------------------- #
+class ClockSampler(object):
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.samples, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append((time.time(), line.strip()))
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self, t0, t1):
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.samples:
+            if ts < t0 or ts > t1 + 0.15:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[0]))
+                mx = max(mx, float(f[1]))
+            except (ValueError, IndexError):
+                continue
+            for k, nm in enumerate(names):
+                if len(f) > 3 + k and f[3 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------- #
+# CPU baseline: the reference's training step as torch-CPU ops (oracle/torch_port.py)
+# --------------------------------------------------------------------------- #
+def cpu_baseline(a, n_timed=0, budget_s=20.0):
+    from oracle.torch_port import MFPort  # cpu_baseline leg: the one place bench.py may run oracle/
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    cores = torch.get_num_threads()
+    g = torch.Generator().manual_seed(SEED)
+    state = {
+        "global_bias": torch.zeros(1),
+        "user_emb.weight": torch.randn(a.users, a.dim, generator=g) * 0.1,
+        "item_emb.weight": torch.randn(a.items, a.dim, generator=g) * 0.1,
+        "user_bias.weight": torch.zeros(a.users, 1),
+        "item_bias.weight": torch.zeros(a.items, 1),
+    }
+    port = MFPort(state, a.optimizer, 0.05, "bpr", 0.0)
+    gen = torch.Generator(device="cpu")
+    gen.manual_seed(SEED)
+    du = zipf_sampler(a.users, ZIPF_A, gen, "cpu")
+    di = zipf_sampler(a.items, ZIPF_A, gen, "cpu")
+    nb = 8
+    batches = [(du(a.batch), di(a.batch), torch.randint(0, a.items, (a.batch,), generator=gen)) for _ in range(nb)]
+    t0 = time.time()
+    port.train_single_batch(batches[0])
+    first = time.time() - t0
+    port.train_single_batch(batches[1])
+    if n_timed <= 0:
+        n_timed = int(max(3, min(40, budget_s / max(first, 1e-3))))
+    times = []
+    for k in range(n_timed):
+        t0 = time.time()
+        port.train_single_batch(batches[k % nb])
+        times.append(time.time() - t0)
+    med = float(np.median(times))
+    return {"value": a.batch / med, "unit": "interactions/s", "cores": cores, "kind": "port",
+            "sample": "%d timed + 2 warm-up train_single_batch calls of the reference's torch-CPU step "
+                      "(oracle/torch_port.py: dense autograd + torch.optim.%s), same shapes as the GPU run, "
+                      "median %.1f ms/step; DataLoader excluded" % (n_timed, a.optimizer.upper(), med * 1e3),
+            "ms_per_step": med * 1e3}
+
+
+def cpu_model_name():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+# --------------------------------------------------------------------------- #
+# reference arm
+# --------------------------------------------------------------------------- #
+def run_reference(a):
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    cb = cpu_baseline(a, n_timed=max(1, min(a.steps, 40)) if a.cpu_steps == 0 else a.cpu_steps)
+    line = {
+        "impl": "reference", "metric": "BPR interactions/sec", "value": cb["value"], "unit": "interactions/s",
+        "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": cb["ms_per_step"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config_dict(a, 1), "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "cpu_model": cpu_model_name(),
+        "e2e": {"value": cb["value"], "unit": "interactions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------- #
+# our arm
+# --------------------------------------------------------------------------- #
+def algorithmic_bytes_per_interaction(dim, optimizer):
+    """SGD 24*D+48; Adam touched rows 72*D+120."""
+    return 24 * dim + 48 if optimizer == "sgd" else 72 * dim + 120
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic():
+    """dram bytes per fwd_bwd launch from the committed ncu --set full capture, if any."""
+    p = os.path.join(ROOT, "profiles", "roofline_latest.json")
+    try:
+        return float(json.load(open(p))["dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
+def run_ours(a):
+    from beta_recsys_b200 import _lib
+    from beta_recsys_b200.engines import MFEngine
+
+    rank, world, local = dist_env()
+    if world != a.gpus:
+        if a.gpus == 1:
+            world, rank, local = 1, 0, 0
+        else:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node %d" % a.gpus)
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+
+    cfg = {"model": dict(device_str="cuda:%d" % local, n_users=a.users, n_items=a.items, emb_dim=a.dim,
+                         batch_size=a.batch, optimizer=a.optimizer, lr=0.05, loss="bpr", adam_mode=a.adam_mode),
+           "system": {"run_dir": "/tmp/brs_bench"}}
+    torch.manual_seed(SEED + rank)
+    import io
+    from contextlib import redirect_stdout
+
+    with redirect_stdout(io.StringIO()):
+        eng = MFEngine(cfg)
+    users, pos, neg = make_batches(a.users, a.items, a.batch, N_PREBUILT, SEED + rank, dev)
+    stream = torch.cuda.current_stream(dev)
+
+    def run_steps(k, first_batch):
+        """k consecutive steps on device-resident batches: one C call per pass over the prebuilt ring."""
+        done = 0
+        b = first_batch % N_PREBUILT
+        while done < k:
+            nb = min(k - done, N_PREBUILT - b)
+            off = b * a.batch
+            out = torch.empty((nb, 4), dtype=torch.float32, device=dev)
+            _lib.check(lib.brs_mf_train_batches(eng._cmodel, eng.optimizer.desc, 0, _lib.ptr(users[off:]),
+                                                _lib.ptr(pos[off:]), _lib.ptr(neg[off:]), nb * a.batch, a.batch, 0.0,
+                                                _lib.ptr(out), stream.cuda_stream), "train_batches")
+            done += nb
+            b = (b + nb) % N_PREBUILT
+        return out
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    launches_per_step = 2 if (a.optimizer == "sgd" or a.adam_mode == "touched") else 4
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    # ---- warm-up + timed region (device-resident inputs) ----
+    run_steps(max(a.warmup, 3), 0)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.time()
+    e0.record(stream)
+    last = run_steps(a.steps, a.warmup)
+    e1.record(stream)
+    barrier()
+    t_wall1 = time.time()
+    ms = e0.elapsed_time(e1)
+    status = float(last[:, 2].max().item())
+    assert status == 0.0, "kernel reported status %r" % status
+    final_loss = float(last[-1, 0].item())
+    # keep the GPU under the same load long enough for nvidia-smi to sample it (untimed)
+    t_load0 = t_wall0
+    while time.time() - t_wall0 < 1.2:
+        run_steps(N_PREBUILT, 0)
+        torch.cuda.synchronize(dev)
+    t_load1 = time.time()
+    clocks = sampler.summary(t_load0, t_load1)
+
+    # ---- per-kernel durations: instrumented replay of the same steps ----
+    n_inst = min(a.steps, 200)
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(n_inst)]
+    out1 = torch.empty(4, dtype=torch.float32, device=dev)
+    for k in range(n_inst):
+        off = ((a.warmup + k) % N_PREBUILT) * a.batch
+        ev[k][0].record(stream)
+        _lib.check(lib.brs_mf_bpr_fwd_bwd(eng._cmodel, _lib.ptr(users[off:]), _lib.ptr(pos[off:]),
+                                          _lib.ptr(neg[off:]), a.batch, 0.0, stream.cuda_stream))
+        ev[k][1].record(stream)
+        _lib.check(lib.brs_mf_apply(eng._cmodel, eng.optimizer.desc, a.batch, _lib.ptr(out1), stream.cuda_stream))
+        ev[k][2].record(stream)
+    torch.cuda.synchronize(dev)
+    t_fwd = float(np.median([e[0].elapsed_time(e[1]) for e in ev]))  # ms
+    t_apply = float(np.median([e[1].elapsed_time(e[2]) for e in ev]))
+
+    # ---- end to end through the public API with HOST index buffers ----
+    e2e = None
+    if not a.no_e2e:
+        n_e2e = min(a.steps, 200)
+        nb_host = min(N_PREBUILT, n_e2e + 3)
+        hu = users[: nb_host * a.batch].cpu().pin_memory()
+        hp = pos[: nb_host * a.batch].cpu().pin_memory()
+        hn = neg[: nb_host * a.batch].cpu().pin_memory()
+
+        def host_batch(k):
+            s = slice((k % nb_host) * a.batch, (k % nb_host + 1) * a.batch)
+            return hu[s], hp[s], hn[s]
+
+        for k in range(3):
+            eng.train_single_batch(host_batch(k))
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record(stream)
+        for k in range(n_e2e):
+            eng.train_single_batch(host_batch(3 + k))  # H2D of 3 index arrays + 2 kernels + 16-byte D2H (sync)
+        s1.record(stream)
+        barrier()
+        ms_e2e = s0.elapsed_time(s1)
+        e2e_ms = torch.tensor([ms_e2e], dtype=torch.float64, device=dev)
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+        e2e = {"value": n_e2e * a.batch * world / (e2e_ms.item() * 1e-3), "unit": "interactions/s",
+               "h2d_bytes_per_step": 3 * 8 * a.batch, "d2h_bytes_per_step": 16, "steps": n_e2e,
+               "api": "MFEngine.train_single_batch((users,pos,neg)) with pinned host LongTensors"}
+    sampler.stop()
+
+    # ---- reduce over ranks ----
+    t = torch.tensor([ms, t_fwd, t_apply], dtype=torch.float64, device=dev)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, t_fwd, t_apply = t.tolist()
+    if rank != 0:
+        return
+    value = a.steps * a.batch * world / (ms * 1e-3)
+    peak, peak_src = measured_peak()
+    alg = algorithmic_bytes_per_interaction(a.dim, a.optimizer) * a.batch
+    achieved = alg / (t_fwd * 1e-3) / 1e9
+    step_achieved = alg / ((t_fwd + t_apply) * 1e-3) / 1e9
+    roofline = {
+        "bound": "hbm", "kernel": "mf_fwd_bwd_kernel (gather 3 rows -> dot/BPR -> red.add 3 gradient rows)",
+        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+        "traffic": ncu_traffic(),
+        "algorithmic_bytes_per_launch": alg, "kernel_ms": t_fwd, "apply_kernel_ms": t_apply,
+        "step_achieved": step_achieved, "step_frac": step_achieved / peak,
+        "note": "achieved = (24*D+48 B per interaction x batch) / median CUDA-event duration of the fwd_bwd launch in an "
+                "instrumented replay of the timed steps; step_* divides the same bytes by fwd_bwd + rows_apply",
+    }
+    line = {
+        "metric": "BPR interactions/sec", "value": value, "unit": "interactions/s", "n_gpus": world,
+        "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_dict(a, world),
+        "roofline": roofline, "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * a.steps,
+        "final_loss": final_loss, "wall_s_timed_region": t_wall1 - t_wall0,
+    }
+    if world == 1 and not a.no_cpu_baseline:
+        cb = cpu_baseline(a, n_timed=a.cpu_steps)
+        line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        line["cpu_model"] = cpu_model_name()
+    print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

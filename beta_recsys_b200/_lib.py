@@ -1,0 +1,117 @@
+"""ctypes binding of libbrs_b200.so (the C ABI declared in include/brs_b200.h).
+
+There is NO fallback: if the library is missing or a call fails, the product
+raises.  PyTorch is used by the callers only to own device memory and streams;
+no torch type crosses this boundary -- only raw device pointers and sizes.
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libbrs_b200.so")
+
+BRS_OK = 0
+SGD, ADAM, RMSPROP = 0, 1, 2
+DENSE, TOUCHED_ROWS = 0, 1
+MAX_ENTITY_TABLES = 4
+STEP_WS_BYTES = 256
+OPT_KINDS = {"sgd": SGD, "adam": ADAM, "rmsprop": RMSPROP}
+
+
+class BrsError(RuntimeError):
+    pass
+
+
+class Opt(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("mode", C.c_int32), ("lr", C.c_double), ("beta1", C.c_double),
+                ("beta2", C.c_double), ("eps", C.c_double), ("alpha", C.c_double)]
+
+
+class Table(C.Structure):
+    _fields_ = [("weight", C.c_void_p), ("grad", C.c_void_p), ("m", C.c_void_p), ("v", C.c_void_p),
+                ("n_rows", C.c_int64), ("dim", C.c_int32), ("pad_", C.c_int32)]
+
+
+class Rowset(C.Structure):
+    _fields_ = [("bits", C.c_void_p), ("list", C.c_void_p), ("count", C.c_void_p), ("n_rows", C.c_int64),
+                ("capacity", C.c_int32), ("pad_", C.c_int32)]
+
+
+class Entity(C.Structure):
+    _fields_ = [("rows", Rowset), ("n_tables", C.c_int32), ("pad_", C.c_int32), ("table", Table * MAX_ENTITY_TABLES)]
+
+
+class DenseParam(C.Structure):
+    _fields_ = [("weight", C.c_void_p), ("grad", C.c_void_p), ("m", C.c_void_p), ("v", C.c_void_p),
+                ("numel", C.c_int64)]
+
+
+class MfModel(C.Structure):
+    _fields_ = [("user", Entity), ("item", Entity), ("global_bias", DenseParam), ("ws", C.c_void_p)]
+
+
+_P = C.c_void_p
+_PROTOTYPES = {
+    # name: (restype, argtypes)
+    "brs_abi_version": (C.c_int, []),
+    "brs_strerror": (C.c_char_p, [C.c_int]),
+    "brs_last_cuda_error": (C.c_char_p, []),
+    "brs_device_info": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                  C.POINTER(C.c_int64)]),
+    "brs_mf_bpr_fwd_bwd": (C.c_int, [C.POINTER(MfModel), _P, _P, _P, C.c_int64, C.c_float, _P]),
+    "brs_mf_bce_fwd_bwd": (C.c_int, [C.POINTER(MfModel), _P, _P, _P, C.c_int64, C.c_float, _P]),
+    "brs_mf_apply": (C.c_int, [C.POINTER(MfModel), C.POINTER(Opt), C.c_int64, _P, _P]),
+    "brs_mf_train_batches": (C.c_int, [C.POINTER(MfModel), C.POINTER(Opt), C.c_int32, _P, _P, _P, C.c_int64,
+                                       C.c_int64, C.c_float, _P, _P]),
+    "brs_mf_predict": (C.c_int, [C.POINTER(MfModel), _P, _P, C.c_int64, _P, _P]),
+    "brs_rows_sgd": (C.c_int, [C.POINTER(Entity), C.c_int32, C.c_double, _P]),
+    "brs_rows_adam": (C.c_int, [C.POINTER(Entity), C.c_int32, C.POINTER(Opt), C.c_int64, _P]),
+    "brs_dense_adam_sweep": (C.c_int, [C.POINTER(Entity), C.c_int32, C.POINTER(Opt), C.c_int64, _P]),
+    "brs_dense_params_step": (C.c_int, [C.POINTER(DenseParam), C.c_int32, C.POINTER(Opt), C.c_int64, _P]),
+    "brs_gather": (C.c_int, [_P, C.c_int64, C.c_int32, _P, C.c_int64, _P, _P]),
+    "brs_scatter_add": (C.c_int, [_P, C.c_int64, C.c_int32, _P, C.c_int64, _P, C.c_float, _P]),
+    "brs_gather_sgd_update": (C.c_int, [_P, C.c_int64, C.c_int32, _P, C.c_int64, C.c_float, _P, _P]),
+}
+
+_lib = None
+
+
+def load():
+    """Load (once) and return the shared library; raise loudly if it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise BrsError(
+            "libbrs_b200.so not found at %s -- build it with `python -m beta_recsys_b200.build` "
+            "(there is no CPU or PyTorch fallback)" % LIB_PATH
+        )
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in _PROTOTYPES.items():
+        fn = getattr(lib, name)  # AttributeError if the ABI lost a symbol
+        fn.restype = res
+        fn.argtypes = args
+    if lib.brs_abi_version() != 1:
+        raise BrsError("libbrs_b200.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def check(status, what=""):
+    if status != BRS_OK:
+        lib = load()
+        msg = lib.brs_strerror(status).decode()
+        if status == -3:
+            msg += ": " + lib.brs_last_cuda_error().decode()
+        raise BrsError("%s failed: %s" % (what or "libbrs_b200 call", msg))
+
+
+def ptr(t):
+    """Raw device pointer of a torch tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def make_opt(optimizer, lr, mode=DENSE):
+    if optimizer not in OPT_KINDS:
+        raise ValueError("unsupported optimizer %r (sgd | adam | rmsprop)" % (optimizer,))
+    return Opt(OPT_KINDS[optimizer], mode, float(lr), 0.9, 0.999, 1e-8, 0.99)

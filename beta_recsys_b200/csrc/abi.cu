@@ -1,0 +1,202 @@
+// Library-level C ABI: status strings, device info, MF step composition, the
+// epoch loop over HBM-resident batches, and the gather / scatter-add micro-ops
+// of BASELINE.json config 5.  See include/brs_b200.h for the contract.
+#include <mutex>
+#include <stdio.h>
+#include <string.h>
+
+#include "common.cuh"
+
+int brs_mf_fwd_bwd_impl(const brs_mf_model* model, int loss_kind, const int64_t* users, const int64_t* items,
+                        const void* third, int64_t batch, float reg_weight, void* stream);
+int brs_apply_impl(const brs_entity* ents, int n_ent, const brs_dense_param* dense, int n_dense,
+                   int dense_grad_from_ws, const brs_opt* opt, void* ws, long long t_explicit, float* out,
+                   long long batch, long long max_rows_hint, void* stream);
+
+namespace {
+char g_cuda_err[512] = "";
+std::mutex g_err_mu;
+int g_sm_count = 0;
+}  // namespace
+
+void brs_set_cuda_error(cudaError_t e, const char* what, int line) {
+    std::lock_guard<std::mutex> lk(g_err_mu);
+    snprintf(g_cuda_err, sizeof(g_cuda_err), "%s (%s) at %s:%d", cudaGetErrorName(e), cudaGetErrorString(e), what, line);
+    (void)cudaGetLastError();
+}
+
+int brs_sm_count() {
+    if (g_sm_count == 0) {
+        int dev = 0, n = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess &&
+            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+            g_sm_count = n;
+        else
+            g_sm_count = 148;  // B200
+    }
+    return g_sm_count;
+}
+
+extern "C" int brs_abi_version(void) { return BRS_ABI_VERSION; }
+
+extern "C" const char* brs_strerror(int status) {
+    switch (status) {
+        case BRS_OK: return "ok";
+        case BRS_ERR_INVALID_ARG: return "invalid argument (null pointer, bad size or misaligned table)";
+        case BRS_ERR_UNSUPPORTED: return "unsupported dimension / optimizer / shape";
+        case BRS_ERR_CUDA: return "CUDA runtime error (see brs_last_cuda_error)";
+        case BRS_ERR_INDEX_RANGE: return "index out of range";
+        case BRS_ERR_NO_DEVICE: return "no CUDA device";
+        default: return "unknown status";
+    }
+}
+
+extern "C" const char* brs_last_cuda_error(void) { return g_cuda_err; }
+
+extern "C" int brs_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, int64_t* l2_bytes) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) {
+        (void)cudaGetLastError();
+        return BRS_ERR_NO_DEVICE;
+    }
+    int v = 0;
+    if (sm_count) {
+        BRS_CUDA_CHECK(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device));
+        *sm_count = v;
+    }
+    if (cc_major) {
+        BRS_CUDA_CHECK(cudaDeviceGetAttribute(&v, cudaDevAttrComputeCapabilityMajor, device));
+        *cc_major = v;
+    }
+    if (cc_minor) {
+        BRS_CUDA_CHECK(cudaDeviceGetAttribute(&v, cudaDevAttrComputeCapabilityMinor, device));
+        *cc_minor = v;
+    }
+    if (l2_bytes) {
+        BRS_CUDA_CHECK(cudaDeviceGetAttribute(&v, cudaDevAttrL2CacheSize, device));
+        *l2_bytes = v;
+    }
+    return BRS_OK;
+}
+
+// ---------------------------------------------------------------------------
+// MF step composition
+// ---------------------------------------------------------------------------
+extern "C" int brs_mf_apply(const brs_mf_model* model, const brs_opt* opt, int64_t batch, float* out_loss_reg,
+                            void* stream) {
+    if (!model || !opt || !model->ws || batch < 0) return BRS_ERR_INVALID_ARG;
+    brs_entity ents[2] = {model->user, model->item};
+    // a batch touches at most `batch` user rows and 2*batch item rows
+    const long long hint = 3 * (long long)batch;
+    return brs_apply_impl(ents, 2, &model->global_bias, 1, /*dense_grad_from_ws=*/1, opt, model->ws, 0, out_loss_reg,
+                          batch, hint, stream);
+}
+
+extern "C" int brs_mf_train_batches(const brs_mf_model* model, const brs_opt* opt, int32_t loss_kind,
+                                    const int64_t* users, const int64_t* items, const void* third, int64_t n,
+                                    int64_t batch, float reg_weight, float* out_loss_reg, void* stream) {
+    if (!model || !opt || !users || !items || !third || n < 0 || batch <= 0 || !out_loss_reg) return BRS_ERR_INVALID_ARG;
+    const size_t third_sz = loss_kind == 0 ? 8 : 4;
+    int64_t b = 0;
+    for (int64_t off = 0; off < n; off += batch, ++b) {
+        const int64_t cur = (n - off < batch) ? (n - off) : batch;
+        int rc = brs_mf_fwd_bwd_impl(model, loss_kind, users + off, items + off, (const char*)third + off * third_sz, cur,
+                                     reg_weight, stream);
+        if (rc != BRS_OK) return rc;
+        rc = brs_mf_apply(model, opt, cur, out_loss_reg + 4 * b, stream);
+        if (rc != BRS_OK) return rc;
+    }
+    return BRS_OK;
+}
+
+// ---------------------------------------------------------------------------
+// gather / scatter-add micro-ops (config 5): warp-group per index, 128-bit accesses
+// ---------------------------------------------------------------------------
+namespace {
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+
+enum { OP_GATHER = 0, OP_SCATTER_ADD = 1, OP_GATHER_SGD = 2 };
+
+template <int LPR, int VPL, int OP>
+__global__ void __launch_bounds__(kThreads) rows_op_kernel(float* __restrict__ table, long long n_rows, int D,
+                                                           const long long* __restrict__ idx, long long n,
+                                                           float* __restrict__ buf, float scale) {
+    constexpr int SPW = 32 / LPR;
+    const int lane = threadIdx.x & 31;
+    const int gl = lane % LPR, grp = lane / LPR;
+    const long long warp_global = (long long)blockIdx.x * kWarps + (threadIdx.x >> 5);
+    const long long n_warps = (long long)gridDim.x * kWarps;
+    for (long long base = warp_global * SPW; base < n; base += n_warps * SPW) {
+        const long long s = base + grp;
+        if (s >= n) continue;
+        const long long r = idx[s];
+        if ((unsigned long long)r >= (unsigned long long)n_rows) continue;
+        float* row = table + r * D;
+        float* b = buf + s * D;
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+            const int col = (v * LPR + gl) * 4;
+            if (col < D) {
+                if (OP == OP_GATHER) {
+                    *(float4*)(b + col) = ld_row4(row + col);
+                } else if (OP == OP_SCATTER_ADD) {
+                    float4 x = *(const float4*)(b + col);
+                    red_add4(row + col, make_float4(scale * x.x, scale * x.y, scale * x.z, scale * x.w));
+                } else {  // gather, hand the row out, apply an SGD-style update in place
+                    float4 x = ld_row4(row + col);
+                    *(float4*)(b + col) = x;
+                    red_add4(row + col, make_float4(-scale * x.x, -scale * x.y, -scale * x.z, -scale * x.w));
+                }
+            }
+        }
+    }
+}
+
+template <int OP>
+int launch_rows_op(float* table, int64_t n_rows, int32_t D, const int64_t* idx, int64_t n, float* buf, float scale,
+                   void* stream) {
+    if (!table || !idx || !buf || n_rows < 0 || n < 0) return BRS_ERR_INVALID_ARG;
+    if (D <= 0 || D % 4 != 0 || D > 512) return BRS_ERR_UNSUPPORTED;
+    if ((((uintptr_t)table | (uintptr_t)buf) & 15) != 0) return BRS_ERR_INVALID_ARG;
+    if (n == 0) return BRS_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+#define BRS_ROWS(LPR, VPL)                                                                                       \
+    do {                                                                                                         \
+        auto k = rows_op_kernel<LPR, VPL, OP>;                                                                   \
+        int per_sm = 1;                                                                                          \
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kThreads, 0);                                  \
+        long long blocks = (n + kWarps * (32 / LPR) - 1) / (kWarps * (32 / LPR));                                \
+        long long grid = (long long)brs_sm_count() * (per_sm < 1 ? 1 : per_sm);                                  \
+        if (grid > blocks) grid = blocks;                                                                        \
+        k<<<(int)grid, kThreads, 0, st>>>(table, n_rows, D, (const long long*)idx, n, buf, scale);               \
+    } while (0)
+    if (D <= 4) BRS_ROWS(1, 1);
+    else if (D <= 8) BRS_ROWS(2, 1);
+    else if (D <= 16) BRS_ROWS(4, 1);
+    else if (D <= 32) BRS_ROWS(8, 1);
+    else if (D <= 64) BRS_ROWS(16, 1);
+    else if (D <= 128) BRS_ROWS(32, 1);
+    else if (D <= 256) BRS_ROWS(32, 2);
+    else if (D <= 384) BRS_ROWS(32, 3);
+    else BRS_ROWS(32, 4);
+#undef BRS_ROWS
+    BRS_CUDA_CHECK(cudaGetLastError());
+    return BRS_OK;
+}
+}  // namespace
+
+extern "C" int brs_gather(const float* table, int64_t n_rows, int32_t dim, const int64_t* idx, int64_t n, float* out,
+                          void* stream) {
+    return launch_rows_op<OP_GATHER>(const_cast<float*>(table), n_rows, dim, idx, n, out, 0.f, stream);
+}
+
+extern "C" int brs_scatter_add(float* table, int64_t n_rows, int32_t dim, const int64_t* idx, int64_t n,
+                               const float* src, float scale, void* stream) {
+    return launch_rows_op<OP_SCATTER_ADD>(table, n_rows, dim, idx, n, const_cast<float*>(src), scale, stream);
+}
+
+extern "C" int brs_gather_sgd_update(float* table, int64_t n_rows, int32_t dim, const int64_t* idx, int64_t n,
+                                     float lr, float* out, void* stream) {
+    return launch_rows_op<OP_GATHER_SGD>(table, n_rows, dim, idx, n, out, lr, stream);
+}

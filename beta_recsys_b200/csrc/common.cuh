@@ -1,0 +1,127 @@
+// Device helpers shared by the sm_100a kernels of libbrs_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/brs_b200.h"
+
+#define BRS_WARP 32
+#define BRS_FULL_MASK 0xffffffffu
+
+// Device scratch behind brs_*_model.ws (BRS_STEP_WS_BYTES, zero-initialised once by the host).
+struct __align__(16) brs_step_ws {
+    double loss_sum;          // sum over samples of the per-sample loss
+    double reg_sum;           // sum over samples of the regularizer numerator
+    float g_global_bias;      // d loss / d global_bias (MF)
+    unsigned int ticket;      // blocks finished in the apply kernel (last one finalises)
+    long long step;           // optimizer step counter t (incremented by apply)
+    unsigned int err_flag;    // set when an index is out of range
+    unsigned int pad_[9];
+};
+static_assert(sizeof(brs_step_ws) <= BRS_STEP_WS_BYTES, "ws layout");
+
+// ---------------------------------------------------------------------------
+// memory ops
+// ---------------------------------------------------------------------------
+// 128-bit gather load.  Rows are re-read by other samples of the batch (Zipf
+// duplicates) so they stay on the default (L2-allocating) path; L1 is bypassed.
+__device__ __forceinline__ float4 ld_row4(const float* p) {
+    float4 r;
+    asm volatile("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+// 128-bit fire-and-forget scatter-add (sm_90+): one L2 reduction per 16 bytes.
+__device__ __forceinline__ void red_add4(float* p, float4 v) {
+    asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+                 "f"(v.w)
+                 : "memory");
+}
+__device__ __forceinline__ void red_add1(float* p, float v) {
+    asm volatile("red.relaxed.gpu.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(BRS_FULL_MASK, v, o);
+    return v;
+}
+// sum across the LANES-wide aligned group the lane belongs to
+template <int LANES>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+    for (int o = LANES / 2; o > 0; o >>= 1) v += __shfl_xor_sync(BRS_FULL_MASK, v, o);
+    return v;
+}
+
+// ---------------------------------------------------------------------------
+// mbarrier + 1-D TMA bulk copy (global -> shared), used to stage index tiles
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// cp.async.bulk (SASS: UBLKCP): bytes % 16 == 0, src/dst 16-byte aligned
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// ---------------------------------------------------------------------------
+// touched-row bookkeeping: first toucher of a row appends it to the entity's list
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void mark_touched(const brs_rowset& rs, long long row) {
+    unsigned int bit = 1u << (row & 31);
+    unsigned int* w = rs.bits + (row >> 5);
+    // cheap read first: hot (Zipf) rows are already marked by the time most samples arrive
+    unsigned int cur = *((volatile unsigned int*)w);
+    if (cur & bit) return;
+    unsigned int old = atomicOr(w, bit);
+    if (!(old & bit)) {
+        int slot = atomicAdd(rs.count, 1);
+        if (slot < rs.capacity) rs.list[slot] = (int)row;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// scalar math exactly as ATen evaluates it in fp32
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+// F.logsigmoid(x) = min(x,0) - log1p(exp(-|x|))
+__device__ __forceinline__ float logsigmoidf_(float x) { return fminf(x, 0.0f) - log1pf(expf(-fabsf(x))); }
+// F.softplus(x), beta 1, threshold 20
+__device__ __forceinline__ float softplusf_(float x) { return x > 20.0f ? x : log1pf(expf(x)); }
+
+#define BRS_CUDA_CHECK(expr)                          \
+    do {                                              \
+        cudaError_t e__ = (expr);                     \
+        if (e__ != cudaSuccess) {                     \
+            brs_set_cuda_error(e__, #expr, __LINE__); \
+            return BRS_ERR_CUDA;                      \
+        }                                             \
+    } while (0)
+
+void brs_set_cuda_error(cudaError_t e, const char* what, int line);
+int brs_sm_count();

@@ -1,0 +1,474 @@
+// MF (matrix factorisation) fused forward + backward for one batch -- sm_100a.
+//
+// Replaces, per batch, the reference's ~45 ATen launches
+//   MF.forward x2            beta_rec/models/mf.py:32-55
+//   bpr_loss / bce_loss      beta_rec/models/torch_engine.py:92-121
+//   loss.backward()          beta_rec/models/mf.py:116-117  (embedding_dense_backward)
+// with ONE kernel: index tiles staged into shared memory by 1-D TMA bulk copies
+// (double-buffered, mbarrier-tracked), 128-bit coalesced gathers of the three
+// embedding rows, group-shuffle dot products, the loss and its closed-form
+// gradient, and 128-bit red.global.add scatter of the three gradient rows into
+// the tables' gradient scratch.  The optimizer update is a separate launch
+// (rows_apply.cu) so that every sample reads PRE-step weights (batch-synchronous
+// semantics of autograd + torch.optim).
+//
+// Thread mapping: a row of D floats is covered by LPR = min(32, D/4) lanes x VPL
+// float4 each, so a warp handles SPW = 32/LPR samples per pass and every global
+// access of a lane group is one contiguous 16*LPR-byte segment.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int kTile = 128;  // samples per staged index tile
+
+enum { LOSS_BPR = 0, LOSS_BCE = 1 };
+
+struct MfArgs {
+    const float* __restrict__ user_emb;
+    const float* __restrict__ item_emb;
+    const float* __restrict__ user_bias;
+    const float* __restrict__ item_bias;
+    const float* __restrict__ global_bias;
+    float* g_user_emb;
+    float* g_item_emb;
+    float* g_user_bias;
+    float* g_item_bias;
+    brs_rowset user_rows;
+    brs_rowset item_rows;
+    brs_step_ws* ws;
+    const long long* users;
+    const long long* items;  // pos items (bpr) / items (bce)
+    const void* third;       // neg items int64 (bpr) / ratings float (bce)
+    long long batch;
+    long long n_users, n_items;
+    int dim;
+    float reg_w;   // engine.reg (0.0 in the reference: mf.py:81-83)
+    float inv_b;   // 1 / batch
+};
+
+struct __align__(16) IdxTile {
+    long long a[kTile];
+    long long b[kTile];
+    long long c[kTile];  // neg ids, or ratings in the first kTile*4 bytes
+};
+
+__device__ __forceinline__ float4 f4_scale(float s, float4 a) { return make_float4(s * a.x, s * a.y, s * a.z, s * a.w); }
+__device__ __forceinline__ float4 f4_fma(float s, float4 a, float4 b) {
+    return make_float4(fmaf(s, a.x, b.x), fmaf(s, a.y, b.y), fmaf(s, a.z, b.z), fmaf(s, a.w, b.w));
+}
+__device__ __forceinline__ float f4_dot(float4 a, float4 b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
+
+// Stage tile `t` of the batch's index lists into `dst`.  TMA path when the slice
+// is a full tile and 16-byte aligned; otherwise (ragged tail / odd views) the
+// block copies it with plain loads and arrives on the same barrier protocol.
+template <int LOSS>
+__device__ __forceinline__ bool stage_tile(const MfArgs& a, long long t, IdxTile* dst, uint64_t* bar) {
+    const long long base = t * kTile;
+    const long long n = min((long long)kTile, a.batch - base);
+    const long long* pa = a.users + base;
+    const long long* pb = a.items + base;
+    const char* pc = (const char*)a.third + base * (LOSS == LOSS_BPR ? 8 : 4);
+    const unsigned bytes_c = (LOSS == LOSS_BPR ? 8u : 4u) * kTile;
+    const bool used_tma = (n == kTile) && ((((uintptr_t)pa | (uintptr_t)pb | (uintptr_t)pc) & 15) == 0);
+    if (used_tma) {
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(bar, 2u * 8u * kTile + bytes_c);
+            tma_load_1d(dst->a, pa, 8u * kTile, bar);
+            tma_load_1d(dst->b, pb, 8u * kTile, bar);
+            tma_load_1d(dst->c, pc, bytes_c, bar);
+        }
+    } else {
+        for (int k = threadIdx.x; k < n; k += kThreads) {
+            dst->a[k] = pa[k];
+            dst->b[k] = pb[k];
+            if (LOSS == LOSS_BPR)
+                dst->c[k] = ((const long long*)pc)[k];
+            else
+                ((float*)dst->c)[k] = ((const float*)pc)[k];
+        }
+    }
+    return used_tma;
+}
+
+template <int LPR, int VPL, bool FULL, int LOSS>
+__global__ void __launch_bounds__(kThreads) mf_fwd_bwd_kernel(const MfArgs a) {
+    constexpr int SPW = 32 / LPR;
+    __shared__ IdxTile s_tile[2];
+    __shared__ __align__(8) uint64_t s_bar[2];
+    __shared__ float s_red[3][kWarps];
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int gl = lane % LPR;   // lane within the row group
+    const int grp = lane / LPR;  // which of the warp's SPW samples
+    const int D = a.dim;
+    const long long n_tiles = (a.batch + kTile - 1) / kTile;
+
+    if (threadIdx.x == 0) {
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const float bg = __ldg(a.global_bias);
+    float loss_acc = 0.f, reg_acc = 0.f, gb_acc = 0.f;
+    unsigned phase_bits = 0u;  // bit b = parity to wait for on s_bar[b]
+    unsigned tma_bits = 0u;    // bit b = s_tile[b] is being filled by TMA
+
+    long long t = blockIdx.x;
+    int buf = 0;
+    if (t < n_tiles && stage_tile<LOSS>(a, t, &s_tile[0], &s_bar[0])) tma_bits |= 1u;
+
+    for (; t < n_tiles; t += gridDim.x, buf ^= 1) {
+        const long long tn = t + gridDim.x;
+        // prefetch the next tile into the other buffer (its previous readers passed
+        // the __syncthreads at the end of the previous iteration)
+        if (tn < n_tiles) {
+            const bool nt = stage_tile<LOSS>(a, tn, &s_tile[buf ^ 1], &s_bar[buf ^ 1]);
+            tma_bits = (tma_bits & ~(1u << (buf ^ 1))) | ((nt ? 1u : 0u) << (buf ^ 1));
+        }
+        if ((tma_bits >> buf) & 1u) {
+            mbar_wait(&s_bar[buf], (phase_bits >> buf) & 1u);
+            phase_bits ^= 1u << buf;
+        } else {
+            __syncthreads();  // plain-copy path: make the block's stores visible
+        }
+        const IdxTile& T = s_tile[buf];
+        const int tile_n = (int)min((long long)kTile, a.batch - t * kTile);
+
+        for (int base = warp * SPW; base < tile_n; base += kWarps * SPW) {
+            const int s = base + grp;
+            bool valid = s < tile_n;
+            const int sc = valid ? s : tile_n - 1;
+            long long u = T.a[sc], i = T.b[sc];
+            long long j = 0;
+            float rating = 0.f;
+            if (LOSS == LOSS_BPR)
+                j = T.c[sc];
+            else
+                rating = ((const float*)T.c)[sc];
+            if ((unsigned long long)u >= (unsigned long long)a.n_users ||
+                (unsigned long long)i >= (unsigned long long)a.n_items ||
+                (unsigned long long)j >= (unsigned long long)a.n_items) {
+                if (valid && gl == 0) atomicOr(&a.ws->err_flag, 1u);  // reference raises IndexError
+                valid = false;
+                u = i = j = 0;
+            }
+            const float* ur = a.user_emb + u * D;
+            const float* ir = a.item_emb + i * D;
+            const float* jr = a.item_emb + j * D;
+
+            float4 ue[VPL], ie[VPL], je[VPL];
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) {
+                const int col = (v * LPR + gl) * 4;
+                const bool on = FULL || col < D;
+                ue[v] = on ? ld_row4(ur + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+                ie[v] = on ? ld_row4(ir + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+                if (LOSS == LOSS_BPR) je[v] = on ? ld_row4(jr + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            const float bu = __ldg(a.user_bias + u);
+            const float bi = __ldg(a.item_bias + i);
+            const float bj = (LOSS == LOSS_BPR) ? __ldg(a.item_bias + j) : 0.f;
+
+            float dp = 0.f, dn = 0.f, uu = 0.f, ii = 0.f, jj = 0.f;
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) {
+                dp += f4_dot(ue[v], ie[v]);
+                uu += f4_dot(ue[v], ue[v]);
+                ii += f4_dot(ie[v], ie[v]);
+                if (LOSS == LOSS_BPR) {
+                    dn += f4_dot(ue[v], je[v]);
+                    jj += f4_dot(je[v], je[v]);
+                }
+            }
+            dp = group_sum<LPR>(dp);
+            if (LOSS == LOSS_BPR) dn = group_sum<LPR>(dn);
+
+            float cu_i, cu_j = 0.f;  // d loss / d z for the (u,i) and (u,j) scores
+            float loss_k;
+            if (LOSS == LOSS_BPR) {
+                // mf.py:43-48 then torch_engine.py:104-105
+                const float sp = sigmoidf_(dp + bu + bi + bg);
+                const float sn = sigmoidf_(dn + bu + bj + bg);
+                const float x = sp - sn;
+                loss_k = -logsigmoidf_(x);
+                const float dx = -a.inv_b / (1.0f + expf(x));  // d/dx of -mean(logsigmoid(x))
+                cu_i = dx * sp * (1.0f - sp);
+                cu_j = -dx * sn * (1.0f - sn);
+            } else {
+                // nn.BCELoss: logs clamped at -100; backward (s-r)/max((1-s)s, 1e-12)/B
+                const float sc_ = sigmoidf_(dp + bu + bi + bg);
+                loss_k = -(rating * fmaxf(logf(sc_), -100.f) + (1.0f - rating) * fmaxf(log1pf(-sc_), -100.f));
+                const float ds = (sc_ - rating) / fmaxf((1.0f - sc_) * sc_, 1e-12f) * a.inv_b;
+                cu_i = ds * sc_ * (1.0f - sc_);
+            }
+
+            if (valid) {
+                // regularizer numerator (mf.py:49-54), one forward call per score
+                const float fwd_calls = (LOSS == LOSS_BPR) ? 2.f : 1.f;
+                reg_acc += fwd_calls * uu + ii + jj;
+                if (gl == 0) {
+                    reg_acc += fwd_calls * bu * bu + bi * bi + bj * bj;
+                    loss_acc += loss_k;
+                    gb_acc += cu_i + cu_j;
+                }
+                const float rw = 2.0f * a.reg_w * a.inv_b;  // d(reg_w*regularizer)/d row = rw * row per forward call
+                float* gu = a.g_user_emb + u * D;
+                float* gi = a.g_item_emb + i * D;
+                float* gj = a.g_item_emb + j * D;
+#pragma unroll
+                for (int v = 0; v < VPL; ++v) {
+                    const int col = (v * LPR + gl) * 4;
+                    if (FULL || col < D) {
+                        float4 du = f4_scale(cu_i, ie[v]);
+                        if (LOSS == LOSS_BPR) du = f4_fma(cu_j, je[v], du);
+                        if (a.reg_w != 0.f) du = f4_fma(fwd_calls * rw, ue[v], du);
+                        red_add4(gu + col, du);
+                        float4 di = f4_scale(cu_i, ue[v]);
+                        if (a.reg_w != 0.f) di = f4_fma(rw, ie[v], di);
+                        red_add4(gi + col, di);
+                        if (LOSS == LOSS_BPR) {
+                            float4 dj = f4_scale(cu_j, ue[v]);
+                            if (a.reg_w != 0.f) dj = f4_fma(rw, je[v], dj);
+                            red_add4(gj + col, dj);
+                        }
+                    }
+                }
+                // biases + touched-row bookkeeping, spread over the first lanes of the group
+                if (gl == 0) {
+                    red_add1(a.g_user_bias + u, cu_i + cu_j + fwd_calls * rw * bu);
+                    mark_touched(a.user_rows, u);
+                }
+                if (gl == 1 % LPR) {
+                    red_add1(a.g_item_bias + i, cu_i + rw * bi);
+                    mark_touched(a.item_rows, i);
+                }
+                if (LOSS == LOSS_BPR && gl == 2 % LPR) {
+                    red_add1(a.g_item_bias + j, cu_j + rw * bj);
+                    mark_touched(a.item_rows, j);
+                }
+            }
+        }
+        __syncthreads();  // everyone is done with s_tile[buf] before it is refilled
+    }
+
+    // block reduction of the scalar outputs -> 3 atomics per block
+    loss_acc = warp_sum(loss_acc);
+    reg_acc = warp_sum(reg_acc);
+    gb_acc = warp_sum(gb_acc);
+    if (lane == 0) {
+        s_red[0][warp] = loss_acc;
+        s_red[1][warp] = reg_acc;
+        s_red[2][warp] = gb_acc;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        float l = lane < kWarps ? s_red[0][lane] : 0.f;
+        float r = lane < kWarps ? s_red[1][lane] : 0.f;
+        float g = lane < kWarps ? s_red[2][lane] : 0.f;
+        l = warp_sum(l);
+        r = warp_sum(r);
+        g = warp_sum(g);
+        if (lane == 0) {
+            atomicAdd(&a.ws->loss_sum, (double)l);
+            atomicAdd(&a.ws->reg_sum, (double)r);
+            atomicAdd(&a.ws->g_global_bias, g);
+        }
+    }
+}
+
+// scores[k] = sigmoid(u.i + b_u + b_i + b_g): MF.predict (mf.py:57-70)
+template <int LPR, int VPL, bool FULL>
+__global__ void __launch_bounds__(kThreads) mf_predict_kernel(const float* __restrict__ user_emb,
+                                                              const float* __restrict__ item_emb,
+                                                              const float* __restrict__ user_bias,
+                                                              const float* __restrict__ item_bias,
+                                                              const float* __restrict__ global_bias, int D,
+                                                              long long n_users, long long n_items,
+                                                              const long long* __restrict__ users,
+                                                              const long long* __restrict__ items, long long n,
+                                                              float* __restrict__ scores, unsigned int* err) {
+    constexpr int SPW = 32 / LPR;
+    const int lane = threadIdx.x & 31;
+    const int gl = lane % LPR, grp = lane / LPR;
+    const long long warp_global = (long long)blockIdx.x * kWarps + (threadIdx.x >> 5);
+    const long long n_warps = (long long)gridDim.x * kWarps;
+    const float bg = __ldg(global_bias);
+    for (long long base = warp_global * SPW; base < n; base += n_warps * SPW) {
+        const long long s = base + grp;
+        bool valid = s < n;
+        long long u = valid ? users[s] : 0, i = valid ? items[s] : 0;
+        if ((unsigned long long)u >= (unsigned long long)n_users || (unsigned long long)i >= (unsigned long long)n_items) {
+            if (valid && gl == 0) atomicOr(err, 1u);
+            valid = false;
+            u = i = 0;
+        }
+        float d = 0.f;
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+            const int col = (v * LPR + gl) * 4;
+            if (FULL || col < D) d += f4_dot(ld_row4(user_emb + u * D + col), ld_row4(item_emb + i * D + col));
+        }
+        d = group_sum<LPR>(d);
+        if (valid && gl == 0) scores[s] = sigmoidf_(d + __ldg(user_bias + u) + __ldg(item_bias + i) + bg);
+    }
+}
+
+int grid_for(const void* kernel, long long work_blocks) {
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0);
+    if (per_sm < 1) per_sm = 1;
+    long long g = (long long)brs_sm_count() * per_sm;  // persistent: one wave of resident blocks
+    if (g > work_blocks) g = work_blocks;
+    return (int)(g < 1 ? 1 : g);
+}
+
+template <int LOSS>
+int launch_fwd_bwd(const MfArgs& a, cudaStream_t st) {
+    const int D = a.dim;
+    const long long n_tiles = (a.batch + kTile - 1) / kTile;
+#define BRS_LAUNCH(LPR, VPL, FULL)                                                      \
+    do {                                                                                \
+        auto k = mf_fwd_bwd_kernel<LPR, VPL, FULL, LOSS>;                               \
+        k<<<grid_for((const void*)k, n_tiles), kThreads, 0, st>>>(a);                   \
+    } while (0)
+    if (D % 4 != 0 || D <= 0 || D > 512) return BRS_ERR_UNSUPPORTED;
+    switch (D) {
+        case 4: BRS_LAUNCH(1, 1, true); break;
+        case 8: BRS_LAUNCH(2, 1, true); break;
+        case 16: BRS_LAUNCH(4, 1, true); break;
+        case 32: BRS_LAUNCH(8, 1, true); break;
+        case 64: BRS_LAUNCH(16, 1, true); break;
+        case 128: BRS_LAUNCH(32, 1, true); break;
+        case 256: BRS_LAUNCH(32, 2, true); break;
+        case 384: BRS_LAUNCH(32, 3, true); break;
+        case 512: BRS_LAUNCH(32, 4, true); break;
+        default:  // any other multiple of 4: next power-of-two lane group, tail lanes idle
+            if (D < 8) BRS_LAUNCH(2, 1, false);
+            else if (D < 16) BRS_LAUNCH(4, 1, false);
+            else if (D < 32) BRS_LAUNCH(8, 1, false);
+            else if (D < 64) BRS_LAUNCH(16, 1, false);
+            else if (D < 128) BRS_LAUNCH(32, 1, false);
+            else if (D < 256) BRS_LAUNCH(32, 2, false);
+            else if (D < 384) BRS_LAUNCH(32, 3, false);
+            else BRS_LAUNCH(32, 4, false);
+    }
+#undef BRS_LAUNCH
+    BRS_CUDA_CHECK(cudaGetLastError());
+    return BRS_OK;
+}
+
+int check_model(const brs_mf_model* m) {
+    if (!m || !m->ws) return BRS_ERR_INVALID_ARG;
+    const brs_table& ue = m->user.table[0];
+    const brs_table& ie = m->item.table[0];
+    if (m->user.n_tables < 2 || m->item.n_tables < 2) return BRS_ERR_INVALID_ARG;
+    if (!ue.weight || !ie.weight || !m->user.table[1].weight || !m->item.table[1].weight || !m->global_bias.weight)
+        return BRS_ERR_INVALID_ARG;
+    if (ue.dim != ie.dim || m->user.table[1].dim != 1 || m->item.table[1].dim != 1) return BRS_ERR_INVALID_ARG;
+    if ((((uintptr_t)ue.weight | (uintptr_t)ie.weight) & 15) != 0) return BRS_ERR_INVALID_ARG;
+    return BRS_OK;
+}
+
+int fill_args(const brs_mf_model* m, MfArgs& a, bool need_grad) {
+    int rc = check_model(m);
+    if (rc != BRS_OK) return rc;
+    a.user_emb = m->user.table[0].weight;
+    a.item_emb = m->item.table[0].weight;
+    a.user_bias = m->user.table[1].weight;
+    a.item_bias = m->item.table[1].weight;
+    a.global_bias = m->global_bias.weight;
+    a.g_user_emb = m->user.table[0].grad;
+    a.g_item_emb = m->item.table[0].grad;
+    a.g_user_bias = m->user.table[1].grad;
+    a.g_item_bias = m->item.table[1].grad;
+    if (need_grad) {
+        if (!a.g_user_emb || !a.g_item_emb || !a.g_user_bias || !a.g_item_bias) return BRS_ERR_INVALID_ARG;
+        if ((((uintptr_t)a.g_user_emb | (uintptr_t)a.g_item_emb) & 15) != 0) return BRS_ERR_INVALID_ARG;
+        if (!m->user.rows.bits || !m->user.rows.list || !m->user.rows.count || !m->item.rows.bits ||
+            !m->item.rows.list || !m->item.rows.count)
+            return BRS_ERR_INVALID_ARG;
+    }
+    a.user_rows = m->user.rows;
+    a.item_rows = m->item.rows;
+    a.ws = (brs_step_ws*)m->ws;
+    a.n_users = m->user.table[0].n_rows;
+    a.n_items = m->item.table[0].n_rows;
+    a.dim = m->user.table[0].dim;
+    return BRS_OK;
+}
+
+}  // namespace
+
+int brs_mf_fwd_bwd_impl(const brs_mf_model* model, int loss_kind, const int64_t* users, const int64_t* items,
+                        const void* third, int64_t batch, float reg_weight, void* stream) {
+    if (!users || !items || !third || batch < 0) return BRS_ERR_INVALID_ARG;
+    MfArgs a;
+    int rc = fill_args(model, a, true);
+    if (rc != BRS_OK) return rc;
+    if (batch == 0) return BRS_OK;
+    a.users = (const long long*)users;
+    a.items = (const long long*)items;
+    a.third = third;
+    a.batch = batch;
+    a.reg_w = reg_weight;
+    a.inv_b = 1.0f / (float)batch;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (loss_kind == LOSS_BPR) return launch_fwd_bwd<LOSS_BPR>(a, st);
+    if (loss_kind == LOSS_BCE) return launch_fwd_bwd<LOSS_BCE>(a, st);
+    return BRS_ERR_INVALID_ARG;
+}
+
+extern "C" int brs_mf_bpr_fwd_bwd(const brs_mf_model* model, const int64_t* users, const int64_t* pos_items,
+                                  const int64_t* neg_items, int64_t batch, float reg_weight, void* stream) {
+    return brs_mf_fwd_bwd_impl(model, LOSS_BPR, users, pos_items, neg_items, batch, reg_weight, stream);
+}
+
+extern "C" int brs_mf_bce_fwd_bwd(const brs_mf_model* model, const int64_t* users, const int64_t* items,
+                                  const float* ratings, int64_t batch, float reg_weight, void* stream) {
+    return brs_mf_fwd_bwd_impl(model, LOSS_BCE, users, items, ratings, batch, reg_weight, stream);
+}
+
+extern "C" int brs_mf_predict(const brs_mf_model* model, const int64_t* users, const int64_t* items, int64_t n,
+                              float* scores, void* stream) {
+    if (!users || !items || !scores || n < 0) return BRS_ERR_INVALID_ARG;
+    MfArgs a;
+    int rc = fill_args(model, a, false);
+    if (rc != BRS_OK) return rc;
+    if (n == 0) return BRS_OK;
+    const int D = a.dim;
+    if (D % 4 != 0 || D <= 0 || D > 512) return BRS_ERR_UNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned int* err = &a.ws->err_flag;
+#define BRS_PRED(LPR, VPL, FULL)                                                                                   \
+    do {                                                                                                           \
+        auto k = mf_predict_kernel<LPR, VPL, FULL>;                                                                \
+        long long blocks = (n + kWarps * (32 / LPR) - 1) / (kWarps * (32 / LPR));                                  \
+        k<<<grid_for((const void*)k, blocks), kThreads, 0, st>>>(a.user_emb, a.item_emb, a.user_bias, a.item_bias, \
+                                                                 a.global_bias, D, a.n_users, a.n_items,           \
+                                                                 (const long long*)users, (const long long*)items, \
+                                                                 n, scores, err);                                  \
+    } while (0)
+    if (D == 4) BRS_PRED(1, 1, true);
+    else if (D == 8) BRS_PRED(2, 1, true);
+    else if (D == 16) BRS_PRED(4, 1, true);
+    else if (D == 32) BRS_PRED(8, 1, true);
+    else if (D == 64) BRS_PRED(16, 1, true);
+    else if (D == 128) BRS_PRED(32, 1, true);
+    else if (D == 256) BRS_PRED(32, 2, true);
+    else if (D < 8) BRS_PRED(2, 1, false);
+    else if (D < 16) BRS_PRED(4, 1, false);
+    else if (D < 32) BRS_PRED(8, 1, false);
+    else if (D < 64) BRS_PRED(16, 1, false);
+    else if (D < 128) BRS_PRED(32, 1, false);
+    else if (D < 256) BRS_PRED(32, 2, false);
+    else if (D <= 384) BRS_PRED(32, 3, false);
+    else BRS_PRED(32, 4, false);
+#undef BRS_PRED
+    BRS_CUDA_CHECK(cudaGetLastError());
+    return BRS_OK;
+}

@@ -1,0 +1,431 @@
+// optimizer.step() for embedding tables -- sm_100a.
+//
+// Replaces torch.optim.{SGD,Adam,RMSprop}.step over dense [N,D] gradients
+// (beta_rec/models/torch_engine.py:23-39, called at beta_rec/models/mf.py:118).
+//
+//  * rows kernels: a warp per TOUCHED row (list built by the fwd/bwd kernel):
+//    read grad row + weight row (+ m, v), update, write back, zero the grad row,
+//    clear the touched bit.  Exact for SGD (g = 0 elsewhere => no change).
+//  * dense sweep: every element of every table, g = 0 for untouched rows --
+//    what the reference's dense Adam/RMSprop actually does each step.
+// The last block to finish also applies the dense parameters (global bias),
+// publishes {loss, regularizer} and resets the step scratch.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int kMaxEntities = 4;
+constexpr int kMaxDense = 16;
+
+struct OptScalars {  // per-step scalars, computed in double like torch does on the host
+    float lr;
+    float one_minus_b1, b2, one_minus_b2;
+    float step_size;  // lr / (1 - b1^t)
+    float bc2_sqrt;   // sqrt(1 - b2^t)
+    float eps;
+    float alpha, one_minus_alpha;
+};
+
+struct OptParams {
+    int kind;
+    double lr, beta1, beta2, eps, alpha;
+};
+
+__device__ __forceinline__ OptScalars make_scalars(const OptParams& o, long long t) {
+    OptScalars s;
+    s.lr = (float)o.lr;
+    s.one_minus_b1 = (float)(1.0 - o.beta1);
+    s.b2 = (float)o.beta2;
+    s.one_minus_b2 = (float)(1.0 - o.beta2);
+    const double bc1 = 1.0 - pow(o.beta1, (double)t);
+    const double bc2 = 1.0 - pow(o.beta2, (double)t);
+    s.step_size = (float)(o.lr / bc1);
+    s.bc2_sqrt = (float)sqrt(bc2);
+    s.eps = (float)o.eps;
+    s.alpha = (float)o.alpha;
+    s.one_minus_alpha = (float)(1.0 - o.alpha);
+    return s;
+}
+
+// one element of torch.optim's single-tensor update
+template <int KIND>
+__device__ __forceinline__ void opt_elem(float& p, float g, float& m, float& v, const OptScalars& s) {
+    if (KIND == BRS_SGD) {
+        p -= s.lr * g;  // sgd.py: param.add_(grad, alpha=-lr)
+    } else if (KIND == BRS_ADAM) {
+        m = m + (g - m) * s.one_minus_b1;                // exp_avg.lerp_(grad, 1-beta1)
+        v = v * s.b2 + s.one_minus_b2 * g * g;           // mul_(beta2).addcmul_(grad, grad, 1-beta2)
+        const float denom = sqrtf(v) / s.bc2_sqrt + s.eps;
+        p -= s.step_size * (m / denom);                  // addcdiv_(exp_avg, denom, -step_size)
+    } else {
+        v = v * s.alpha + s.one_minus_alpha * g * g;     // rmsprop.py, momentum 0, not centered
+        p -= s.lr * (g / (sqrtf(v) + s.eps));
+    }
+}
+
+struct ApplyArgs {
+    brs_entity ent[kMaxEntities];
+    int n_ent;
+    brs_dense_param dense[kMaxDense];
+    int n_dense;
+    int dense_grad_from_ws;  // dense[0].grad is ws->g_global_bias (MF)
+    OptParams opt;
+    brs_step_ws* ws;    // may be NULL for the stand-alone generic entry points
+    long long t_explicit;  // step number when ws == NULL
+    float* out;         // device brs_step_out (float[4]) or NULL
+    double inv_batch;
+    int advance_step;   // last block: ws->step += 1, reset sums
+};
+
+template <int KIND>
+__device__ __forceinline__ void update_row(const brs_table& tb, long long row, int lane, const OptScalars& s) {
+    const int d = tb.dim;
+    float* w = tb.weight + row * d;
+    float* g = tb.grad + row * d;
+    float* m = (KIND == BRS_ADAM) ? tb.m + row * d : nullptr;
+    float* v = (KIND != BRS_SGD) ? tb.v + row * d : nullptr;
+    if ((d & 3) == 0) {
+        for (int c = lane * 4; c < d; c += 128) {
+            float4 gv = *(const float4*)(g + c);
+            float4 wv = *(const float4*)(w + c);
+            float4 mv = make_float4(0.f, 0.f, 0.f, 0.f), vv = mv;
+            if (KIND == BRS_ADAM) mv = *(const float4*)(m + c);
+            if (KIND != BRS_SGD) vv = *(const float4*)(v + c);
+            opt_elem<KIND>(wv.x, gv.x, mv.x, vv.x, s);
+            opt_elem<KIND>(wv.y, gv.y, mv.y, vv.y, s);
+            opt_elem<KIND>(wv.z, gv.z, mv.z, vv.z, s);
+            opt_elem<KIND>(wv.w, gv.w, mv.w, vv.w, s);
+            *(float4*)(w + c) = wv;
+            if (KIND == BRS_ADAM) *(float4*)(m + c) = mv;
+            if (KIND != BRS_SGD) *(float4*)(v + c) = vv;
+            *(float4*)(g + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    } else {
+        for (int c = lane; c < d; c += 32) {
+            float gv = g[c], wv = w[c];
+            float mv = (KIND == BRS_ADAM) ? m[c] : 0.f;
+            float vv = (KIND != BRS_SGD) ? v[c] : 0.f;
+            opt_elem<KIND>(wv, gv, mv, vv, s);
+            w[c] = wv;
+            if (KIND == BRS_ADAM) m[c] = mv;
+            if (KIND != BRS_SGD) v[c] = vv;
+            g[c] = 0.f;
+        }
+    }
+}
+
+// dense parameters + publication of the step's scalars; run by the LAST block only
+template <int KIND>
+__device__ void finalize(const ApplyArgs& a, const OptScalars& s) {
+    for (int k = 0; k < a.n_dense; ++k) {
+        const brs_dense_param& dp = a.dense[k];
+        for (long long e = threadIdx.x; e < dp.numel; e += kThreads) {
+            float g;
+            if (k == 0 && a.dense_grad_from_ws)
+                g = a.ws->g_global_bias;
+            else
+                g = dp.grad[e];
+            float w = dp.weight[e];
+            float m = (KIND == BRS_ADAM) ? dp.m[e] : 0.f;
+            float v = (KIND != BRS_SGD) ? dp.v[e] : 0.f;
+            opt_elem<KIND>(w, g, m, v, s);
+            dp.weight[e] = w;
+            if (KIND == BRS_ADAM) dp.m[e] = m;
+            if (KIND != BRS_SGD) dp.v[e] = v;
+            if (!(k == 0 && a.dense_grad_from_ws) && dp.grad) dp.grad[e] = 0.f;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && a.ws) {
+        if (a.out) {  // brs_step_out
+            a.out[0] = (float)(a.ws->loss_sum * a.inv_batch);
+            a.out[1] = (float)(a.ws->reg_sum * a.inv_batch);
+            a.out[2] = (float)a.ws->err_flag;  // 0 ok | 1 index out of range | 2 touched-list overflow
+            a.out[3] = 0.f;
+        }
+        if (a.advance_step) {
+            a.ws->err_flag = 0u;
+            a.ws->loss_sum = 0.0;
+            a.ws->reg_sum = 0.0;
+            a.ws->g_global_bias = 0.f;
+            a.ws->step += 1;
+        }
+        a.ws->ticket = 0u;
+    }
+}
+
+template <int KIND>
+__device__ __forceinline__ bool last_block(const ApplyArgs& a) {
+    __shared__ bool s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int prev = atomicAdd(&a.ws->ticket, 1u);
+        s_last = (prev == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last) __threadfence();
+    return s_last;
+}
+
+// ---- touched rows only ------------------------------------------------------
+template <int KIND>
+__global__ void __launch_bounds__(kThreads) rows_apply_kernel(const ApplyArgs a) {
+    __shared__ OptScalars s_opt;
+    __shared__ int s_cnt[kMaxEntities + 1];
+    if (threadIdx.x == 0) {
+        const long long t = a.ws ? a.ws->step + 1 : a.t_explicit;
+        s_opt = make_scalars(a.opt, t);
+        int acc = 0;
+        for (int e = 0; e < a.n_ent; ++e) {
+            s_cnt[e] = acc;
+            int c = *a.ent[e].rows.count;
+            if (c > a.ent[e].rows.capacity) {  // list too small for this batch: rows would be lost
+                c = a.ent[e].rows.capacity;
+                if (a.ws) atomicOr(&a.ws->err_flag, 2u);
+            }
+            acc += c;
+        }
+        s_cnt[a.n_ent] = acc;
+    }
+    __syncthreads();
+    const OptScalars s = s_opt;
+    const int lane = threadIdx.x & 31;
+    const int total = s_cnt[a.n_ent];
+    for (int r = blockIdx.x * kWarps + (threadIdx.x >> 5); r < total; r += gridDim.x * kWarps) {
+        int e = 0;
+        while (e + 1 < a.n_ent && r >= s_cnt[e + 1]) ++e;
+        const brs_entity& en = a.ent[e];
+        const long long row = en.rows.list[r - s_cnt[e]];
+        for (int k = 0; k < en.n_tables; ++k) update_row<KIND>(en.table[k], row, lane, s);
+        if (lane == 0) atomicAnd(en.rows.bits + (row >> 5), ~(1u << (row & 31)));
+    }
+    if (a.ws) {
+        if (last_block<KIND>(a)) {
+            if (threadIdx.x < a.n_ent) *a.ent[threadIdx.x].rows.count = 0;
+            finalize<KIND>(a, s);
+        }
+    } else if (blockIdx.x == 0 && a.n_dense) {
+        finalize<KIND>(a, s);
+    }
+}
+
+// ---- every row (reference-exact Adam / RMSprop) -----------------------------
+// grid-stride over float4 vectors (or scalars when dim % 4 != 0) of one table
+template <int KIND>
+__device__ __forceinline__ void sweep_table(const brs_table& tb, const unsigned int* __restrict__ bits,
+                                            const OptScalars& s, long long tid, long long nthreads) {
+    const int d = tb.dim;
+    if ((d & 3) == 0) {
+        const int vpr = d >> 2;
+        const long long nvec = tb.n_rows * vpr;
+        const int shift = (vpr & (vpr - 1)) == 0 ? __ffs(vpr) - 1 : -1;
+        for (long long i = tid; i < nvec; i += nthreads) {
+            const long long row = shift >= 0 ? (i >> shift) : (nvec < (1ll << 31) ? (long long)((unsigned)i / (unsigned)vpr) : i / vpr);
+            const bool touched = (bits[row >> 5] >> (row & 31)) & 1u;
+            float4 gv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (touched) {
+                gv = ((const float4*)tb.grad)[i];
+                ((float4*)tb.grad)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            float4 wv = ((const float4*)tb.weight)[i];
+            float4 mv = make_float4(0.f, 0.f, 0.f, 0.f), vv = mv;
+            if (KIND == BRS_ADAM) mv = ((const float4*)tb.m)[i];
+            if (KIND != BRS_SGD) vv = ((const float4*)tb.v)[i];
+            opt_elem<KIND>(wv.x, gv.x, mv.x, vv.x, s);
+            opt_elem<KIND>(wv.y, gv.y, mv.y, vv.y, s);
+            opt_elem<KIND>(wv.z, gv.z, mv.z, vv.z, s);
+            opt_elem<KIND>(wv.w, gv.w, mv.w, vv.w, s);
+            ((float4*)tb.weight)[i] = wv;
+            if (KIND == BRS_ADAM) ((float4*)tb.m)[i] = mv;
+            if (KIND != BRS_SGD) ((float4*)tb.v)[i] = vv;
+        }
+    } else {
+        const long long n = tb.n_rows * d;
+        for (long long i = tid; i < n; i += nthreads) {
+            const long long row = i / d;
+            const bool touched = (bits[row >> 5] >> (row & 31)) & 1u;
+            float g = 0.f;
+            if (touched) {
+                g = tb.grad[i];
+                tb.grad[i] = 0.f;
+            }
+            float w = tb.weight[i];
+            float m = (KIND == BRS_ADAM) ? tb.m[i] : 0.f;
+            float v = (KIND != BRS_SGD) ? tb.v[i] : 0.f;
+            opt_elem<KIND>(w, g, m, v, s);
+            tb.weight[i] = w;
+            if (KIND == BRS_ADAM) tb.m[i] = m;
+            if (KIND != BRS_SGD) tb.v[i] = v;
+        }
+    }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(kThreads) dense_sweep_kernel(const ApplyArgs a) {
+    __shared__ OptScalars s_opt;
+    if (threadIdx.x == 0) s_opt = make_scalars(a.opt, a.ws ? a.ws->step + 1 : a.t_explicit);
+    __syncthreads();
+    const OptScalars s = s_opt;
+    const long long tid = (long long)blockIdx.x * kThreads + threadIdx.x;
+    const long long nthreads = (long long)gridDim.x * kThreads;
+    for (int e = 0; e < a.n_ent; ++e)
+        for (int k = 0; k < a.ent[e].n_tables; ++k) sweep_table<KIND>(a.ent[e].table[k], a.ent[e].rows.bits, s, tid, nthreads);
+    if (a.ws) {
+        if (last_block<KIND>(a)) finalize<KIND>(a, s);
+    } else if (blockIdx.x == 0 && a.n_dense) {
+        finalize<KIND>(a, s);
+    }
+}
+
+// clears the touched bits after a dense sweep (the sweep itself reads them)
+__global__ void __launch_bounds__(kThreads) rowset_clear_kernel(const ApplyArgs a) {
+    for (int e = 0; e < a.n_ent; ++e) {
+        const brs_rowset& rs = a.ent[e].rows;
+        int c = *rs.count;
+        if (c > rs.capacity) c = rs.capacity;
+        for (int r = blockIdx.x * kThreads + threadIdx.x; r < c; r += gridDim.x * kThreads) {
+            const long long row = rs.list[r];
+            atomicAnd(rs.bits + (row >> 5), ~(1u << (row & 31)));
+        }
+    }
+}
+
+__global__ void rowset_reset_counts_kernel(const ApplyArgs a) {
+    if (threadIdx.x < a.n_ent) *a.ent[threadIdx.x].rows.count = 0;
+}
+
+int validate_entities(const brs_entity* ents, int n, int kind) {
+    if (n < 0 || n > kMaxEntities || (n > 0 && !ents)) return BRS_ERR_INVALID_ARG;
+    for (int e = 0; e < n; ++e) {
+        const brs_entity& en = ents[e];
+        if (en.n_tables < 0 || en.n_tables > BRS_MAX_ENTITY_TABLES) return BRS_ERR_INVALID_ARG;
+        if (!en.rows.bits || !en.rows.list || !en.rows.count) return BRS_ERR_INVALID_ARG;
+        for (int k = 0; k < en.n_tables; ++k) {
+            const brs_table& t = en.table[k];
+            if (!t.weight || !t.grad || t.dim <= 0 || t.n_rows < 0) return BRS_ERR_INVALID_ARG;
+            if (kind == BRS_ADAM && (!t.m || !t.v)) return BRS_ERR_INVALID_ARG;
+            if (kind == BRS_RMSPROP && !t.v) return BRS_ERR_INVALID_ARG;
+            if ((t.dim & 3) == 0 && ((((uintptr_t)t.weight | (uintptr_t)t.grad | (uintptr_t)t.m | (uintptr_t)t.v) & 15) != 0))
+                return BRS_ERR_INVALID_ARG;
+        }
+    }
+    return BRS_OK;
+}
+
+int validate_dense(const brs_dense_param* p, int n, int kind, bool grad_from_ws) {
+    if (n < 0 || n > kMaxDense || (n > 0 && !p)) return BRS_ERR_INVALID_ARG;
+    for (int k = 0; k < n; ++k) {
+        if (!p[k].weight || p[k].numel < 0) return BRS_ERR_INVALID_ARG;
+        if (!(k == 0 && grad_from_ws) && !p[k].grad) return BRS_ERR_INVALID_ARG;
+        if (kind == BRS_ADAM && (!p[k].m || !p[k].v)) return BRS_ERR_INVALID_ARG;
+        if (kind == BRS_RMSPROP && !p[k].v) return BRS_ERR_INVALID_ARG;
+    }
+    return BRS_OK;
+}
+
+void fill_opt(ApplyArgs& a, const brs_opt* opt) {
+    a.opt.kind = opt->kind;
+    a.opt.lr = opt->lr;
+    a.opt.beta1 = opt->beta1;
+    a.opt.beta2 = opt->beta2;
+    a.opt.eps = opt->eps;
+    a.opt.alpha = opt->alpha;
+}
+
+int persistent_grid(const void* kernel) {
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0);
+    if (per_sm < 1) per_sm = 1;
+    return brs_sm_count() * per_sm;
+}
+
+template <int KIND>
+int launch_apply(const ApplyArgs& a, int mode, long long max_rows_hint, cudaStream_t st) {
+    if (KIND != BRS_SGD && mode == BRS_DENSE) {
+        auto k = dense_sweep_kernel<KIND>;
+        k<<<persistent_grid((const void*)k), kThreads, 0, st>>>(a);
+        rowset_clear_kernel<<<brs_sm_count(), kThreads, 0, st>>>(a);
+        rowset_reset_counts_kernel<<<1, 32, 0, st>>>(a);
+    } else {
+        auto k = rows_apply_kernel<KIND>;
+        int grid = persistent_grid((const void*)k);
+        long long need = (max_rows_hint + kWarps - 1) / kWarps;
+        if (need < 1) need = 1;
+        if (grid > need) grid = (int)need;
+        k<<<grid, kThreads, 0, st>>>(a);
+    }
+    BRS_CUDA_CHECK(cudaGetLastError());
+    return BRS_OK;
+}
+
+}  // namespace
+
+// shared with abi.cu: apply `opt` to entities + dense params (+ finalize through ws)
+int brs_apply_impl(const brs_entity* ents, int n_ent, const brs_dense_param* dense, int n_dense,
+                   int dense_grad_from_ws, const brs_opt* opt, void* ws, long long t_explicit, float* out,
+                   long long batch, long long max_rows_hint, void* stream) {
+    if (!opt) return BRS_ERR_INVALID_ARG;
+    int rc = validate_entities(ents, n_ent, opt->kind);
+    if (rc != BRS_OK) return rc;
+    rc = validate_dense(dense, n_dense, opt->kind, dense_grad_from_ws != 0);
+    if (rc != BRS_OK) return rc;
+    ApplyArgs a;
+    memset(&a, 0, sizeof(a));
+    for (int e = 0; e < n_ent; ++e) a.ent[e] = ents[e];
+    a.n_ent = n_ent;
+    for (int k = 0; k < n_dense; ++k) a.dense[k] = dense[k];
+    a.n_dense = n_dense;
+    a.dense_grad_from_ws = dense_grad_from_ws;
+    fill_opt(a, opt);
+    a.ws = (brs_step_ws*)ws;
+    a.t_explicit = t_explicit;
+    a.out = out;
+    a.inv_batch = batch > 0 ? 1.0 / (double)batch : 0.0;
+    a.advance_step = ws ? 1 : 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (opt->kind) {
+        case BRS_SGD: return launch_apply<BRS_SGD>(a, BRS_TOUCHED_ROWS, max_rows_hint, st);
+        case BRS_ADAM: return launch_apply<BRS_ADAM>(a, opt->mode, max_rows_hint, st);
+        case BRS_RMSPROP: return launch_apply<BRS_RMSPROP>(a, opt->mode, max_rows_hint, st);
+        default: return BRS_ERR_UNSUPPORTED;
+    }
+}
+
+extern "C" int brs_rows_sgd(const brs_entity* entities, int32_t n_entities, double lr, void* stream) {
+    brs_opt o;
+    memset(&o, 0, sizeof(o));
+    o.kind = BRS_SGD;
+    o.lr = lr;
+    long long hint = 0;
+    for (int e = 0; entities && e < n_entities && e < kMaxEntities; ++e) hint += entities[e].rows.capacity;
+    return brs_apply_impl(entities, n_entities, nullptr, 0, 0, &o, nullptr, 1, nullptr, 0, hint, stream);
+}
+
+extern "C" int brs_rows_adam(const brs_entity* entities, int32_t n_entities, const brs_opt* opt, int64_t t,
+                             void* stream) {
+    if (!opt || t < 1) return BRS_ERR_INVALID_ARG;
+    brs_opt o = *opt;
+    o.mode = BRS_TOUCHED_ROWS;
+    long long hint = 0;
+    for (int e = 0; entities && e < n_entities && e < kMaxEntities; ++e) hint += entities[e].rows.capacity;
+    return brs_apply_impl(entities, n_entities, nullptr, 0, 0, &o, nullptr, t, nullptr, 0, hint, stream);
+}
+
+extern "C" int brs_dense_adam_sweep(const brs_entity* entities, int32_t n_entities, const brs_opt* opt, int64_t t,
+                                    void* stream) {
+    if (!opt || t < 1 || opt->kind == BRS_SGD) return BRS_ERR_INVALID_ARG;
+    brs_opt o = *opt;
+    o.mode = BRS_DENSE;
+    return brs_apply_impl(entities, n_entities, nullptr, 0, 0, &o, nullptr, t, nullptr, 0, 0, stream);
+}
+
+extern "C" int brs_dense_params_step(const brs_dense_param* params, int32_t n_params, const brs_opt* opt, int64_t t,
+                                     void* stream) {
+    if (!opt || t < 1) return BRS_ERR_INVALID_ARG;
+    brs_opt o = *opt;
+    o.mode = BRS_TOUCHED_ROWS;
+    return brs_apply_impl(nullptr, 0, params, n_params, 0, &o, nullptr, t, nullptr, 0, 0, stream);
+}

@@ -1,0 +1,191 @@
+/*
+ * brs_b200.h -- C ABI of libbrs_b200.so, the sm_100a hot path under
+ * beta_rec's MatrixFactorization.train() / NeuCF.train() / LightGCN.train().
+ *
+ * The reference (beta-team/beta-recsys) is pure Python and has no FFI: its seam
+ * is the duck-typed engine contract consumed by TrainEngine._train
+ * (beta_rec/core/train_engine.py:225-240).  The Python engines in
+ * beta_recsys_b200/engines mirror that contract and call ONLY the functions
+ * declared here, through ctypes (INTEGRATION.md shows the binding).
+ *
+ * Conventions
+ *   - every function returns BRS_OK (0) or a negative brs_status; no exceptions
+ *     cross the ABI; brs_strerror() names a status.
+ *   - all pointers inside the descriptor structs are DEVICE pointers owned by
+ *     the caller (PyTorch allocates them); nothing is allocated, freed or
+ *     retained by the library.  Tables are updated IN PLACE.
+ *   - stream-ordered, no hidden synchronisation; `stream` is a cudaStream_t
+ *     passed as void* (0 = legacy default stream).
+ *   - floats are fp32, indices are int64 (torch.LongTensor) exactly as the
+ *     reference passes them (beta_rec/data/data_loaders.py:43-49).
+ *   - batch-synchronous semantics: every sample of a batch reads PRE-step
+ *     weights, duplicate rows' gradients are summed, then one optimizer update
+ *     is applied (what autograd + torch.optim do in the reference).
+ */
+#ifndef BRS_B200_H
+#define BRS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BRS_ABI_VERSION 1
+
+typedef enum brs_status {
+    BRS_OK = 0,
+    BRS_ERR_INVALID_ARG = -1,   /* NULL pointer, negative size, misaligned table */
+    BRS_ERR_UNSUPPORTED = -2,   /* dim / optimizer / layer shape the kernels do not cover */
+    BRS_ERR_CUDA = -3,          /* a CUDA runtime call failed; see brs_last_cuda_error() */
+    BRS_ERR_INDEX_RANGE = -4,   /* reserved: index outside its table (debug check) */
+    BRS_ERR_NO_DEVICE = -5      /* no sm_100 device / driver */
+} brs_status;
+
+/* ---- optimizers: ModelEngine.set_optimizer (beta_rec/models/torch_engine.py:23-39) ---- */
+typedef enum brs_opt_kind { BRS_SGD = 0, BRS_ADAM = 1, BRS_RMSPROP = 2 } brs_opt_kind;
+
+/* BRS_DENSE reproduces the reference exactly: nn.Embedding(sparse=False) gives dense
+ * gradients, so torch.optim.Adam/RMSprop update EVERY row every step (rows with zero
+ * gradient keep moving through the decaying first moment).  BRS_TOUCHED_ROWS updates only
+ * rows present in the batch ("lazy" Adam): exact for SGD, NOT equivalent for Adam/RMSprop
+ * after the first step -- offered as a named, non-default mode. */
+typedef enum brs_opt_mode { BRS_DENSE = 0, BRS_TOUCHED_ROWS = 1 } brs_opt_mode;
+
+/* hyper-parameters are doubles: torch.optim keeps them as Python floats and derives the
+ * per-step scalars (lr / (1 - beta1^t), sqrt(1 - beta2^t)) in double before casting to fp32 */
+typedef struct brs_opt {
+    int32_t kind;         /* brs_opt_kind */
+    int32_t mode;         /* brs_opt_mode (ignored for SGD: always touched rows, which is exact) */
+    double lr;
+    double beta1, beta2;  /* Adam (torch defaults 0.9, 0.999) */
+    double eps;           /* Adam / RMSprop (1e-8) */
+    double alpha;         /* RMSprop (0.99) */
+} brs_opt;
+
+/* ---- one embedding table + its per-step gradient scratch and optimizer state ---- */
+typedef struct brs_table {
+    float *weight;   /* [n_rows, dim] row-major; 16-byte aligned when dim % 4 == 0 */
+    float *grad;     /* [n_rows, dim] gradient accumulator; all-zero between steps */
+    float *m;        /* Adam exp_avg            (NULL for SGD / RMSprop) */
+    float *v;        /* Adam exp_avg_sq / RMSprop square_avg (NULL for SGD) */
+    int64_t n_rows;
+    int32_t dim;
+    int32_t pad_;
+} brs_table;
+
+/* ---- rows of one entity (users or items) touched by the current step ---- */
+typedef struct brs_rowset {
+    uint32_t *bits;  /* [(n_rows+31)/32] touched bitmap; all-zero between steps */
+    int32_t *list;   /* [capacity] touched row ids, unordered */
+    int32_t *count;  /* [1] number of valid entries in list; zero between steps */
+    int64_t n_rows;
+    int32_t capacity; /* >= min(n_rows, occurrences per batch) */
+    int32_t pad_;
+} brs_rowset;
+
+#define BRS_MAX_ENTITY_TABLES 4
+/* an entity = one id space (users / items) + the tables indexed by it */
+typedef struct brs_entity {
+    brs_rowset rows;
+    int32_t n_tables;
+    int32_t pad_;
+    brs_table table[BRS_MAX_ENTITY_TABLES];
+} brs_entity;
+
+/* dense (non-embedding) parameters: global bias, Linear weights/biases.  Updated densely. */
+typedef struct brs_dense_param {
+    float *weight, *grad, *m, *v;
+    int64_t numel;
+} brs_dense_param;
+
+/* device scratch shared by the kernels of one engine: 256 bytes, zero-initialised once */
+#define BRS_STEP_WS_BYTES 256
+
+/* what a step publishes (device memory, 4 floats): the two floats
+ * MFEngine.train_single_batch returns (beta_rec/models/mf.py:119) + a status word */
+typedef struct brs_step_out {
+    float loss;         /* batch loss (mean over the batch) */
+    float regularizer;  /* MF regularizer (mf.py:49-54); 0 for other models */
+    float status;       /* 0 ok | 1 an index was outside its table (the reference raises IndexError)
+                           | 2 touched-row list capacity exceeded */
+    float reserved;
+} brs_step_out;
+
+/* ---- MF: beta_rec/models/mf.py (MF module + MFEngine) ---- */
+typedef struct brs_mf_model {
+    brs_entity user;              /* table[0] = user_emb [U,D], table[1] = user_bias [U,1] */
+    brs_entity item;              /* table[0] = item_emb [I,D], table[1] = item_bias [I,1] */
+    brs_dense_param global_bias;  /* numel 1 */
+    void *ws;                     /* BRS_STEP_WS_BYTES of device scratch */
+} brs_mf_model;
+
+/* library / device */
+int brs_abi_version(void);
+const char *brs_strerror(int status);
+const char *brs_last_cuda_error(void);
+int brs_device_info(int device, int *sm_count, int *cc_major, int *cc_minor, int64_t *l2_bytes);
+
+/*
+ * MF forward + backward for one BPR batch (replaces MF.forward x2 + ModelEngine.bpr_loss +
+ * loss.backward(): beta_rec/models/mf.py:32-55,102-107,116-117; torch_engine.py:92-106).
+ *   score = sigmoid(u.i + b_u + b_i + b_g)            (sigmoid BEFORE the BPR difference)
+ *   loss  = -mean(logsigmoid(score_pos - score_neg));  regularizer as mf.py:49-54 for both calls
+ * Accumulates d(loss + reg_weight*regularizer)/d(row) into table.grad, records touched rows
+ * in the rowsets, and adds the batch's loss / regularizer sums into ws.  One fused kernel.
+ */
+int brs_mf_bpr_fwd_bwd(const brs_mf_model *model, const int64_t *users, const int64_t *pos_items,
+                       const int64_t *neg_items, int64_t batch, float reg_weight, void *stream);
+
+/* Same for loss == "bce" (beta_rec/models/mf.py:108-111; torch_engine.py:108-121, nn.BCELoss). */
+int brs_mf_bce_fwd_bwd(const brs_mf_model *model, const int64_t *users, const int64_t *items,
+                       const float *ratings, int64_t batch, float reg_weight, void *stream);
+
+/*
+ * optimizer.step() + the two .item() results (beta_rec/models/mf.py:118-119): applies `opt`
+ * to the rows recorded by the preceding *_fwd_bwd call (and, in BRS_DENSE mode with
+ * Adam/RMSprop, to every other row with g = 0), clears the gradient scratch / rowsets,
+ * writes the step's brs_step_out to `out` (device) and resets ws.
+ */
+int brs_mf_apply(const brs_mf_model *model, const brs_opt *opt, int64_t batch, float *out /* brs_step_out */,
+                 void *stream);
+
+/*
+ * MFEngine.train_an_epoch's inner loop (beta_rec/models/mf.py:132-136) over index arrays
+ * already resident in HBM: for b in range(ceil(n/batch)): fwd_bwd + apply on
+ * [b*batch, min((b+1)*batch, n)).  loss_kind 0 = bpr (third = neg item ids, int64),
+ * 1 = bce (third = ratings, float).  out is device brs_step_out[n_batches].
+ */
+int brs_mf_train_batches(const brs_mf_model *model, const brs_opt *opt, int32_t loss_kind,
+                         const int64_t *users, const int64_t *items, const void *third, int64_t n,
+                         int64_t batch, float reg_weight, float *out /* brs_step_out[] */, void *stream);
+
+/* MF.predict / MF.forward under no_grad (beta_rec/models/mf.py:57-70): scores[k] = sigmoid(...) */
+int brs_mf_predict(const brs_mf_model *model, const int64_t *users, const int64_t *items, int64_t n,
+                   float *scores, void *stream);
+
+/* ---- generic row optimizers on entities (K6 in SURVEY.md section 2b) ---- */
+/* touched rows only: p -= lr*g (exactly what torch.optim.SGD does, g = 0 elsewhere) */
+int brs_rows_sgd(const brs_entity *entities, int32_t n_entities, double lr, void *stream);
+/* touched rows only, Adam with explicit step number t (1-based) */
+int brs_rows_adam(const brs_entity *entities, int32_t n_entities, const brs_opt *opt, int64_t t, void *stream);
+/* every row of every table: reference-exact Adam / RMSprop (g = 0 for untouched rows) */
+int brs_dense_adam_sweep(const brs_entity *entities, int32_t n_entities, const brs_opt *opt, int64_t t,
+                         void *stream);
+/* dense parameters (Linear layers, global bias); clears their grads */
+int brs_dense_params_step(const brs_dense_param *params, int32_t n_params, const brs_opt *opt, int64_t t,
+                          void *stream);
+
+/* ---- embedding gather / scatter-add micro-ops (BASELINE.json config 5) ---- */
+int brs_gather(const float *table, int64_t n_rows, int32_t dim, const int64_t *idx, int64_t n, float *out,
+               void *stream);
+int brs_scatter_add(float *table, int64_t n_rows, int32_t dim, const int64_t *idx, int64_t n, const float *src,
+                    float scale, void *stream);
+/* table[idx[k]] -= lr * src[k] after gathering: gather + SGD update micro-op */
+int brs_gather_sgd_update(float *table, int64_t n_rows, int32_t dim, const int64_t *idx, int64_t n, float lr,
+                          float *out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BRS_B200_H */

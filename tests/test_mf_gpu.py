@@ -1,0 +1,402 @@
+"""GPU parity tests for the MF path: the CUDA engine (through the C ABI) against
+(a) golden vectors produced by the reference itself and (b) the numpy oracle on
+seeded inputs, plus edge cases and full-size (BASELINE.json config 2) checks.
+
+Tolerance: 1e-5 of each tensor's scale (north-star fp32 budget); for
+Adam/RMSprop the ill-conditioned division is handled as documented in
+tests/test_oracle_golden.py (moments tight, update formula tight).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import cf_oracle as O
+from tests.golden_util import Golden, max_rel_err, names
+from tests.test_oracle_golden import BUDGET, check_adaptive_step, check_params_adaptive
+
+pytestmark = pytest.mark.gpu
+
+
+def make_engine(n_users, n_items, d, batch, optimizer, lr, loss="bpr", adam_mode="dense", reg=None, state=None):
+    from beta_recsys_b200.engines import MFEngine
+
+    cfg = {"model": dict(device_str="cuda:0", n_users=n_users, n_items=n_items, emb_dim=d, batch_size=batch,
+                         optimizer=optimizer, lr=lr, loss=loss, adam_mode=adam_mode),
+           "system": {"run_dir": "/tmp/brs_test"}}
+    if reg is not None:
+        cfg["reg"] = reg  # the reference reads the TOP-LEVEL key (mf.py:81-83)
+        cfg["model"]["reg"] = reg
+    eng = MFEngine(cfg)
+    if state is not None:
+        with torch.no_grad():
+            for k, v in eng.model.state_dict().items():
+                v.copy_(torch.from_numpy(state[k]))
+    return eng
+
+
+def snap(eng):
+    return {k: v.detach().cpu().numpy().copy() for k, v in eng.model.state_dict().items()}
+
+
+def opt_snap(eng):
+    out = {"m": {}, "v": {}}
+    for name, st in eng.optimizer.state.items():
+        for kind in ("m", "v"):
+            if kind in st:
+                out[kind][name] = st[kind].detach().cpu().numpy().copy()
+    return out
+
+
+def cuda_batch(*arrs):
+    return tuple(torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in arrs)
+
+
+def random_state(rng, n_users, n_items, d, bias=0.1):
+    return {
+        "global_bias": np.array([0.03], dtype=np.float32),
+        "user_emb.weight": rng.normal(0, 0.1, (n_users, d)).astype(np.float32),
+        "item_emb.weight": rng.normal(0, 0.1, (n_items, d)).astype(np.float32),
+        "user_bias.weight": rng.normal(0, bias, (n_users, 1)).astype(np.float32),
+        "item_bias.weight": rng.normal(0, bias, (n_items, 1)).astype(np.float32),
+    }
+
+
+def zipf_ids(rng, n, size, a=1.05):
+    """Zipf(a) over a seeded permutation of ids (SURVEY.md section 8d synthetic inputs)."""
+    ranks = np.arange(1, n + 1, dtype=np.float64)
+    p = ranks ** (-a)
+    p /= p.sum()
+    perm = rng.permutation(n)
+    return perm[rng.choice(n, size=size, p=p)].astype(np.int64)
+
+
+# --------------------------------------------------------------------------- #
+# (a) against the reference's own outputs
+# --------------------------------------------------------------------------- #
+@pytest.mark.parametrize("name", names("mf_"))
+def test_mf_matches_reference_golden(name):
+    g = Golden(name)
+    m, b = g.meta, g.batch
+    adaptive = m["optimizer"] in ("adam", "rmsprop")
+    eng = make_engine(m["n_users"], m["n_items"], m["emb_dim"], m["batch"], m["optimizer"], m["lr"], m["loss"],
+                      state=g.init)
+    for t in range(5):
+        before = snap(eng)
+        last = b["neg"][t] if m["loss"] == "bpr" else b["ratings"][t]
+        loss, reg = eng.train_single_batch(cuda_batch(b["users"][t], b["pos"][t], last))
+        lt = 1e-5 if (not adaptive or t == 0) else 1e-3
+        assert abs(loss - g.out["loss"][t]) <= lt * max(1, abs(g.out["loss"][t])), (t, loss)
+        assert abs(reg - g.out["reg"][t]) <= lt * max(1, abs(g.out["reg"][t])), (t, reg)
+        if t == 0:
+            if adaptive:
+                check_adaptive_step(before, snap(eng), opt_snap(eng), g.group("opt1"), m["optimizer"], m["lr"], 1)
+                check_params_adaptive(snap(eng), g.group("after1"), before, m["lr"], 1)
+            else:
+                for k, v in g.group("after1").items():
+                    assert max_rel_err(snap(eng)[k], v) <= BUDGET, (k, max_rel_err(snap(eng)[k], v))
+    if adaptive:
+        check_params_adaptive(snap(eng), g.group("after5"), None, m["lr"], 5)
+    else:
+        for k, v in g.group("after5").items():
+            assert max_rel_err(snap(eng)[k], v) <= BUDGET, (k, max_rel_err(snap(eng)[k], v))
+
+
+# --------------------------------------------------------------------------- #
+# (b) against the oracle on seeded inputs
+# --------------------------------------------------------------------------- #
+@pytest.mark.parametrize("d", [4, 8, 12, 32, 64, 100, 128, 256, 384, 512])
+@pytest.mark.parametrize("loss", ["bpr", "bce"])
+def test_mf_sgd_all_dims_vs_oracle(d, loss):
+    rng = np.random.default_rng(d)
+    nu, ni, bsz = 700, 500, 1000  # ragged: 1000 = 7 full tiles + 104
+    p = random_state(rng, nu, ni, d)
+    st = O.new_opt_state(p, "sgd")
+    eng = make_engine(nu, ni, d, bsz, "sgd", 0.05, loss, state=p)
+    for t in range(3):
+        u, i = zipf_ids(rng, nu, bsz), zipf_ids(rng, ni, bsz)
+        third = rng.integers(0, ni, bsz) if loss == "bpr" else (rng.random(bsz) < 0.3).astype(np.float32)
+        l, r = eng.train_single_batch(cuda_batch(u, i, third))
+        ol, orr = O.mf_train_single_batch(p, st, (u, i, third), loss, "sgd", 0.05, 0.0)
+        assert abs(l - ol) <= 1e-5 * max(1, abs(ol)) and abs(r - orr) <= 1e-5 * max(1, abs(orr)), (t, l, ol, r, orr)
+    got = snap(eng)
+    for k in p:
+        assert max_rel_err(got[k], p[k]) <= BUDGET, (k, max_rel_err(got[k], p[k]))
+
+
+@pytest.mark.parametrize("optimizer", ["adam", "rmsprop"])
+@pytest.mark.parametrize("d", [64, 128])
+def test_mf_dense_adaptive_step_vs_oracle(optimizer, d):
+    """Reference-exact mode: every row is updated every step (zero-gradient rows
+    keep moving through exp_avg).  Step 1 is compared with the conditioning-aware
+    checks; then the m/v of rows NOT in the second batch must have decayed exactly."""
+    rng = np.random.default_rng(7)
+    nu, ni, bsz, lr = 900, 600, 512, 0.01
+    p = random_state(rng, nu, ni, d)
+    st = O.new_opt_state(p, optimizer)
+    eng = make_engine(nu, ni, d, bsz, optimizer, lr, "bpr", state=p)
+    u, i, j = zipf_ids(rng, nu, bsz), zipf_ids(rng, ni, bsz), rng.integers(0, ni, bsz)
+    before = snap(eng)
+    l, r = eng.train_single_batch(cuda_batch(u, i, j))
+    ol, orr = O.mf_train_single_batch(p, st, (u, i, j), "bpr", optimizer, lr, 0.0)
+    assert abs(l - ol) <= 1e-5 and abs(r - orr) <= 1e-5 * max(1, orr)
+    ref_opt = {f"{kind}/{k}": v for kind in ("m", "v") if kind in st for k, v in st[kind].items()}
+    check_adaptive_step(before, snap(eng), opt_snap(eng), ref_opt, optimizer, lr, 1)
+    check_params_adaptive(snap(eng), p, before, lr, 1)
+    # second step touching a disjoint set of users: the first batch's rows must still move (Adam)
+    u2 = np.setdiff1d(np.arange(nu), u)[:bsz]
+    u2 = np.resize(u2, bsz)
+    opt1 = opt_snap(eng)
+    p1 = snap(eng)
+    eng.train_single_batch(cuda_batch(u2, i, j))
+    opt2, p2 = opt_snap(eng), snap(eng)
+    rows = np.setdiff1d(u, u2)
+    assert rows.size > 0
+    if optimizer == "adam":
+        m1, m2 = opt1["m"]["user_emb.weight"][rows], opt2["m"]["user_emb.weight"][rows]
+        assert max_rel_err(m2, m1 * np.float32(0.9)) <= 1e-6  # lerp towards g = 0
+        assert np.abs(p2["user_emb.weight"][rows] - p1["user_emb.weight"][rows]).max() > 0  # dense Adam moves them
+    v1, v2 = opt1["v"]["user_emb.weight"][rows], opt2["v"]["user_emb.weight"][rows]
+    decay = np.float32(0.999 if optimizer == "adam" else 0.99)
+    assert max_rel_err(v2, v1 * decay) <= 1e-6
+
+
+def test_mf_adam_touched_mode_only_moves_batch_rows():
+    rng = np.random.default_rng(3)
+    nu, ni, d, bsz = 400, 300, 64, 128
+    p = random_state(rng, nu, ni, d)
+    eng = make_engine(nu, ni, d, bsz, "adam", 0.01, "bpr", adam_mode="touched", state=p)
+    u, i, j = rng.integers(0, 200, bsz), rng.integers(0, ni, bsz), rng.integers(0, ni, bsz)
+    eng.train_single_batch(cuda_batch(u, i, j))
+    u2 = rng.integers(200, 400, bsz)
+    p1 = snap(eng)
+    eng.train_single_batch(cuda_batch(u2, i, j))
+    p2 = snap(eng)
+    rows = np.unique(u)
+    assert np.array_equal(p1["user_emb.weight"][rows], p2["user_emb.weight"][rows])  # lazy: untouched rows frozen
+
+
+def test_mf_reg_weight_gradient_vs_oracle():
+    """engine.reg != 0 only when the TOP-LEVEL config carries 'reg' (mf.py:81-83)."""
+    rng = np.random.default_rng(11)
+    nu, ni, d, bsz = 300, 200, 64, 256
+    p = random_state(rng, nu, ni, d)
+    st = O.new_opt_state(p, "sgd")
+    eng = make_engine(nu, ni, d, bsz, "sgd", 0.05, "bpr", reg=0.01, state=p)
+    assert eng.reg == 0.01
+    u, i, j = rng.integers(0, nu, bsz), rng.integers(0, ni, bsz), rng.integers(0, ni, bsz)
+    l, r = eng.train_single_batch(cuda_batch(u, i, j))
+    ol, orr = O.mf_train_single_batch(p, st, (u, i, j), "bpr", "sgd", 0.05, 0.01)
+    assert abs(l - ol) <= 1e-5 and abs(r - orr) <= 1e-5 * max(1, orr)
+    got = snap(eng)
+    for k in p:
+        assert max_rel_err(got[k], p[k]) <= BUDGET, k
+
+
+# --------------------------------------------------------------------------- #
+# edge cases
+# --------------------------------------------------------------------------- #
+@pytest.mark.parametrize("bsz", [1, 2, 31, 127, 128, 129, 257])
+def test_mf_ragged_batch_sizes(bsz):
+    rng = np.random.default_rng(bsz)
+    nu, ni, d = 64, 48, 32
+    p = random_state(rng, nu, ni, d)
+    st = O.new_opt_state(p, "sgd")
+    eng = make_engine(nu, ni, d, 512, "sgd", 0.05, "bpr", state=p)
+    u, i, j = rng.integers(0, nu, bsz), rng.integers(0, ni, bsz), rng.integers(0, ni, bsz)
+    l, r = eng.train_single_batch(cuda_batch(u, i, j))
+    ol, orr = O.mf_train_single_batch(p, st, (u, i, j), "bpr", "sgd", 0.05, 0.0)
+    assert abs(l - ol) <= 1e-5 and abs(r - orr) <= 1e-5 * max(1, orr)
+    got = snap(eng)
+    for k in p:
+        assert max_rel_err(got[k], p[k]) <= BUDGET, k
+
+
+def test_mf_unaligned_index_views_and_cpu_inputs():
+    """8-byte-aligned (not 16) index views take the non-TMA staging path; CPU tensors are moved."""
+    rng = np.random.default_rng(5)
+    nu, ni, d, bsz = 500, 400, 128, 640
+    p = random_state(rng, nu, ni, d)
+    st = O.new_opt_state(p, "sgd")
+    eng = make_engine(nu, ni, d, bsz, "sgd", 0.05, "bpr", state=p)
+    u, i, j = (rng.integers(0, n, bsz + 1) for n in (nu, ni, ni))
+    tu, ti, tj = cuda_batch(u, i, j)
+    l, _ = eng.train_single_batch((tu[1:], ti[1:], tj[1:]))  # offset by one int64
+    ol, _ = O.mf_train_single_batch(p, st, (u[1:], i[1:], j[1:]), "bpr", "sgd", 0.05, 0.0)
+    assert abs(l - ol) <= 1e-5
+    l, _ = eng.train_single_batch((torch.from_numpy(u[:-1]), torch.from_numpy(i[:-1]), torch.from_numpy(j[:-1])))
+    ol, _ = O.mf_train_single_batch(p, st, (u[:-1], i[:-1], j[:-1]), "bpr", "sgd", 0.05, 0.0)
+    assert abs(l - ol) <= 1e-5
+    got = snap(eng)
+    for k in p:
+        assert max_rel_err(got[k], p[k]) <= BUDGET, k
+
+
+def test_mf_all_duplicates_and_pos_equals_neg():
+    rng = np.random.default_rng(9)
+    nu, ni, d, bsz = 50, 40, 128, 512
+    p = random_state(rng, nu, ni, d)
+    st = O.new_opt_state(p, "sgd")
+    eng = make_engine(nu, ni, d, bsz, "sgd", 0.05, "bpr", state=p)
+    u = np.full(bsz, 7, dtype=np.int64)
+    i = np.full(bsz, 3, dtype=np.int64)
+    j = np.where(np.arange(bsz) % 2 == 0, 3, 5).astype(np.int64)  # half the samples have pos == neg
+    l, r = eng.train_single_batch(cuda_batch(u, i, j))
+    ol, orr = O.mf_train_single_batch(p, st, (u, i, j), "bpr", "sgd", 0.05, 0.0)
+    assert abs(l - ol) <= 1e-5 and abs(r - orr) <= 1e-5 * max(1, orr)
+    got = snap(eng)
+    for k in p:
+        assert max_rel_err(got[k], p[k]) <= BUDGET, k
+
+
+def test_mf_out_of_range_index_raises_and_engine_recovers():
+    rng = np.random.default_rng(1)
+    nu, ni, d, bsz = 30, 20, 16, 64
+    p = random_state(rng, nu, ni, d)
+    eng = make_engine(nu, ni, d, bsz, "sgd", 0.05, "bpr", state=p)
+    u, i, j = rng.integers(0, nu, bsz), rng.integers(0, ni, bsz), rng.integers(0, ni, bsz)
+    bad = u.copy()
+    bad[5] = nu  # one past the end
+    with pytest.raises(IndexError):
+        eng.train_single_batch(cuda_batch(bad, i, j))
+    neg = j.copy()
+    neg[0] = -1
+    with pytest.raises(IndexError):
+        eng.train_single_batch(cuda_batch(u, i, neg))
+    eng.train_single_batch(cuda_batch(u, i, j))  # still usable afterwards
+
+
+def test_mf_unsupported_loss_and_dim():
+    from beta_recsys_b200 import BrsError
+
+    eng = make_engine(10, 10, 8, 4, "sgd", 0.1, "hinge")
+    with pytest.raises(RuntimeError, match="Unsupported loss type"):
+        eng.train_single_batch(cuda_batch(np.zeros(4, np.int64), np.zeros(4, np.int64), np.zeros(4, np.int64)))
+    eng = make_engine(10, 10, 6, 4, "sgd", 0.1, "bpr")  # dim % 4 != 0
+    with pytest.raises(BrsError, match="unsupported"):
+        eng.train_single_batch(cuda_batch(np.zeros(4, np.int64), np.zeros(4, np.int64), np.zeros(4, np.int64)))
+
+
+def test_mf_predict_and_forward_match_oracle():
+    rng = np.random.default_rng(2)
+    nu, ni, d = 200, 150, 64
+    p = random_state(rng, nu, ni, d)
+    eng = make_engine(nu, ni, d, 64, "sgd", 0.05, state=p)
+    u, i = rng.integers(0, nu, 333), rng.integers(0, ni, 333)
+    s = eng.model.predict(u, i)  # numpy in, device tensor out (eval_engine.py:258-273 moves it to CPU)
+    os_, oreg = O.mf_forward(p, u, i)
+    assert s.is_cuda and max_rel_err(s.cpu().numpy(), os_) <= 1e-6
+    s2, reg = eng.model.forward(cuda_batch(u, i))
+    assert max_rel_err(s2.cpu().numpy(), os_) <= 1e-6 and abs(float(reg) - oreg) <= 1e-5 * oreg
+
+
+def test_mf_checkpoint_roundtrip_keeps_reference_layout(tmp_path):
+    rng = np.random.default_rng(4)
+    eng = make_engine(40, 30, 16, 32, "adam", 0.01, state=random_state(rng, 40, 30, 16))
+    path = str(tmp_path / "mf.model")
+    eng.save_checkpoint(path)
+    sd = torch.load(path)
+    assert sorted(sd) == sorted(["global_bias", "user_emb.weight", "item_emb.weight", "user_bias.weight",
+                                 "item_bias.weight"])
+    assert sd["user_emb.weight"].shape == (40, 16) and sd["item_bias.weight"].shape == (30, 1)
+    eng2 = make_engine(40, 30, 16, 32, "adam", 0.01)
+    eng2.resume_checkpoint(path)
+    for k, v in snap(eng).items():
+        assert np.array_equal(snap(eng2)[k], v)
+    # the resumed engine trains (kernels still point at live storage)
+    u, i, j = (rng.integers(0, n, 32) for n in (40, 30, 30))
+    eng2.train_single_batch(cuda_batch(u, i, j))
+    assert not np.array_equal(snap(eng2)["user_emb.weight"], snap(eng)["user_emb.weight"])
+
+
+# --------------------------------------------------------------------------- #
+# epoch loop
+# --------------------------------------------------------------------------- #
+class _PairwiseDataset(torch.utils.data.Dataset):
+    """Same shape as beta_rec.data.data_loaders.PairwiseNegativeDataset."""
+
+    def __init__(self, u, p, n):
+        self.user_tensor, self.pos_item_tensor, self.neg_item_tensor = u, p, n
+
+    def __getitem__(self, k):
+        return self.user_tensor[k], self.pos_item_tensor[k], self.neg_item_tensor[k]
+
+    def __len__(self):
+        return self.user_tensor.size(0)
+
+
+def test_train_an_epoch_fast_path_equals_reference_loader_order():
+    """ML-100k-shaped plumbing run (BASELINE config 1 shape): the epoch fast path
+    trains the batches the DataLoader would yield, in its order, and matches the
+    oracle fed by an identically-seeded DataLoader."""
+    rng = np.random.default_rng(2020)
+    nu, ni, d, bsz, n = 943, 1682, 64, 400, 5000
+    p = random_state(rng, nu, ni, d, bias=0.0)
+    u, i, j = zipf_ids(rng, nu, n), zipf_ids(rng, ni, n), rng.integers(0, ni, n)
+    ds = _PairwiseDataset(*cuda_batch(u, i, j))
+    eng = make_engine(nu, ni, d, bsz, "sgd", 0.05, "bpr", state=p)
+    torch.manual_seed(123)
+    eng.train_an_epoch(torch.utils.data.DataLoader(ds, batch_size=bsz, shuffle=True), epoch_id=0)
+    # oracle driven by the same loader (per-sample __getitem__ path, like the reference)
+    st = O.new_opt_state(p, "sgd")
+    torch.manual_seed(123)
+    cpu_ds = _PairwiseDataset(torch.from_numpy(u), torch.from_numpy(i), torch.from_numpy(j))
+    n_batches = 0
+    for bu, bi, bj in torch.utils.data.DataLoader(cpu_ds, batch_size=bsz, shuffle=True):
+        O.mf_train_single_batch(p, st, (bu.numpy(), bi.numpy(), bj.numpy()), "bpr", "sgd", 0.05, 0.0)
+        n_batches += 1
+    assert n_batches == 13  # last batch ragged (5000 = 12*400 + 200)
+    got = snap(eng)
+    for k in p:
+        assert max_rel_err(got[k], p[k]) <= BUDGET, (k, max_rel_err(got[k], p[k]))
+
+
+def test_train_an_epoch_generic_iterable_path():
+    rng = np.random.default_rng(6)
+    nu, ni, d, bsz = 100, 80, 32, 64
+    p = random_state(rng, nu, ni, d)
+    st = O.new_opt_state(p, "sgd")
+    eng = make_engine(nu, ni, d, bsz, "sgd", 0.05, "bpr", state=p)
+    batches = [tuple(rng.integers(0, n, bsz) for n in (nu, ni, ni)) for _ in range(4)]
+    eng.train_an_epoch([cuda_batch(*b) for b in batches], epoch_id=1)
+    for b in batches:
+        O.mf_train_single_batch(p, st, b, "bpr", "sgd", 0.05, 0.0)
+    got = snap(eng)
+    for k in p:
+        assert max_rel_err(got[k], p[k]) <= BUDGET, k
+
+
+# --------------------------------------------------------------------------- #
+# BASELINE.json config 2 at full size: 1M x 100k, D=128, B=65536
+# --------------------------------------------------------------------------- #
+def test_mf_full_size_config2_vs_oracle_and_properties():
+    rng = np.random.default_rng(2020)
+    nu, ni, d, bsz, lr = 1_000_000, 100_000, 128, 65536, 0.05
+    eng = make_engine(nu, ni, d, bsz, "sgd", lr, "bpr")
+    with torch.no_grad():
+        eng.model.user_bias.weight.normal_(0, 0.05)
+        eng.model.item_bias.weight.normal_(0, 0.05)
+    before = snap(eng)
+    u, i, j = zipf_ids(rng, nu, bsz), zipf_ids(rng, ni, bsz), rng.integers(0, ni, bsz)
+    l, r = eng.train_single_batch(cuda_batch(u, i, j))
+    after = snap(eng)
+    # oracle on the same inputs (sparse scatter keeps this to seconds)
+    loss, reg, g = O.mf_bpr_loss_grads(before, u, i, j)
+    assert abs(l - loss) <= 1e-5 * max(1, loss) and abs(r - reg) <= 1e-5 * max(1, reg)
+    for k in before:
+        want = before[k] - np.float32(lr) * g[k]
+        assert max_rel_err(after[k], want) <= BUDGET, (k, max_rel_err(after[k], want))
+    # properties: rows outside the batch are bit-identical; scratch is clean again
+    mask = np.ones(nu, dtype=bool)
+    mask[u] = False
+    assert np.array_equal(after["user_emb.weight"][mask], before["user_emb.weight"][mask])
+    mask = np.ones(ni, dtype=bool)
+    mask[i] = False
+    mask[j] = False
+    assert np.array_equal(after["item_emb.weight"][mask], before["item_emb.weight"][mask])
+    for ent in (eng._user, eng._item):
+        assert int(ent.count.item()) == 0 and int(ent.bits.abs().sum().item()) == 0
+        for gbuf in ent.grads:
+            assert float(gbuf.abs().max().item()) == 0.0
+    # idempotence of the bookkeeping: a second identical step sees the same pre-step semantics
+    l2, _ = eng.train_single_batch(cuda_batch(u, i, j))
+    assert l2 < l  # one SGD step on the same batch lowers its loss
