@@ -49,6 +49,8 @@ def parse():
     ap.add_argument("--items", type=int, default=N_ITEMS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--profile", action="store_true",
+                    help="short run for ncu: no e2e / cpu baseline / clock-load loop (numbers printed are NOT bench values)")
     ap.add_argument("--cpu-steps", type=int, default=0, help="timed CPU steps (0 = auto, ~10-30 s)")
     return ap.parse_args()
 
@@ -323,14 +325,14 @@ def run_ours(a):
     final_loss = float(last[-1, 0].item())
     # keep the GPU under the same load long enough for nvidia-smi to sample it (untimed)
     t_load0 = t_wall0
-    while time.time() - t_wall0 < 1.2:
+    while not a.profile and time.time() - t_wall0 < 1.2:
         run_steps(N_PREBUILT, 0)
         torch.cuda.synchronize(dev)
     t_load1 = time.time()
     clocks = sampler.summary(t_load0, t_load1)
 
     # ---- per-kernel durations: instrumented replay of the same steps ----
-    n_inst = min(a.steps, 200)
+    n_inst = min(a.steps, 200) if not a.profile else 3
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(n_inst)]
     out1 = torch.empty(4, dtype=torch.float32, device=dev)
     for k in range(n_inst):
@@ -421,6 +423,8 @@ def run_ours(a):
 
 def main():
     a = parse()
+    if a.profile:
+        a.no_e2e = a.no_cpu_baseline = True
     if a.impl == "reference":
         run_reference(a)
     else:
