@@ -33,7 +33,7 @@ class Table(C.Structure):
 
 
 class Rowset(C.Structure):
-    _fields_ = [("bits", C.c_void_p), ("list", C.c_void_p), ("count", C.c_void_p), ("n_rows", C.c_int64),
+    _fields_ = [("slot_map", C.c_void_p), ("list", C.c_void_p), ("count", C.c_void_p), ("n_rows", C.c_int64),
                 ("capacity", C.c_int32), ("pad_", C.c_int32)]
 
 
@@ -50,6 +50,21 @@ class MfModel(C.Structure):
     _fields_ = [("user", Entity), ("item", Entity), ("global_bias", DenseParam), ("ws", C.c_void_p)]
 
 
+NCF_GMF, NCF_MLP, NCF_NEUMF = 0, 1, 2
+NCF_MAX_LAYERS = 6
+
+
+class NcfModel(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("n_layers", C.c_int32), ("emb_dim", C.c_int32), ("mlp_dim", C.c_int32),
+                ("user", Entity), ("item", Entity),
+                ("fc_weight", DenseParam * NCF_MAX_LAYERS), ("fc_bias", DenseParam * NCF_MAX_LAYERS),
+                ("out_weight", DenseParam), ("out_bias", DenseParam),
+                ("act", C.c_void_p * (NCF_MAX_LAYERS + 1)), ("dact", C.c_void_p * (NCF_MAX_LAYERS + 1)),
+                ("mfv", C.c_void_p), ("dz", C.c_void_p), ("max_batch", C.c_int64), ("ws", C.c_void_p)]
+
+
+EXTRA_STRUCTS = {"brs_ncf_model": NcfModel}
+
 _P = C.c_void_p
 _PROTOTYPES = {
     # name: (restype, argtypes)
@@ -64,6 +79,15 @@ _PROTOTYPES = {
     "brs_mf_train_batches": (C.c_int, [C.POINTER(MfModel), C.POINTER(Opt), C.c_int32, _P, _P, _P, C.c_int64,
                                        C.c_int64, C.c_float, _P, _P]),
     "brs_mf_predict": (C.c_int, [C.POINTER(MfModel), _P, _P, C.c_int64, _P, _P]),
+    "brs_ncf_fwd_bwd": (C.c_int, [C.POINTER(NcfModel), _P, _P, _P, C.c_int64, _P]),
+    "brs_ncf_apply": (C.c_int, [C.POINTER(NcfModel), C.POINTER(Opt), C.c_int64, _P, _P]),
+    "brs_ncf_predict": (C.c_int, [C.POINTER(NcfModel), _P, _P, C.c_int64, _P, _P]),
+    "brs_ncf_train_batches": (C.c_int, [C.POINTER(NcfModel), C.POINTER(Opt), _P, _P, _P, C.c_int64, C.c_int64, _P,
+                                        _P]),
+    "brs_mlp_fwd": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _P]),
+    "brs_mlp_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int32, C.c_int32, _P]),
+    "brs_rows_assign": (C.c_int, [C.POINTER(Rowset), _P, C.c_int64, _P, _P]),
+    "brs_rows_scatter_grad": (C.c_int, [C.POINTER(Entity), C.c_int32, _P, C.c_int64, _P, C.c_float, _P]),
     "brs_rows_sgd": (C.c_int, [C.POINTER(Entity), C.c_int32, C.c_double, _P]),
     "brs_rows_adam": (C.c_int, [C.POINTER(Entity), C.c_int32, C.POINTER(Opt), C.c_int64, _P]),
     "brs_dense_adam_sweep": (C.c_int, [C.POINTER(Entity), C.c_int32, C.POINTER(Opt), C.c_int64, _P]),

@@ -4,24 +4,34 @@
 //   MF.forward x2            beta_rec/models/mf.py:32-55
 //   bpr_loss / bce_loss      beta_rec/models/torch_engine.py:92-121
 //   loss.backward()          beta_rec/models/mf.py:116-117  (embedding_dense_backward)
-// with ONE kernel: index tiles staged into shared memory by 1-D TMA bulk copies
-// (double-buffered, mbarrier-tracked), 128-bit coalesced gathers of the three
-// embedding rows, group-shuffle dot products, the loss and its closed-form
-// gradient, and 128-bit red.global.add scatter of the three gradient rows into
-// the tables' gradient scratch.  The optimizer update is a separate launch
+// with a slot-assignment pre-pass (rows_apply.cu: one thread per index) and ONE
+// fused kernel: the tile's index lists staged into shared memory by 1-D TMA bulk
+// copies (mbarrier-tracked), 128-bit coalesced gathers of the three embedding
+// rows, group-shuffle dot products, the loss and its closed-form gradient, and
+// 128-bit red.global.add scatter of the three gradient rows into the COMPACT,
+// L2-resident gradient scratch.  The optimizer update is a separate launch
 // (rows_apply.cu) so that every sample reads PRE-step weights (batch-synchronous
 // semantics of autograd + torch.optim).
+//
+// Shape of the launch (from the round-1 ncu capture: the kernel is latency-bound,
+// not atomic- or bandwidth-bound): one 64-sample tile per 128-thread block so a
+// 65536-sample batch is 1024 co-resident blocks; each warp owns 16 samples and
+// keeps two passes (2 x SPW samples, 6 row loads per lane) in flight; nothing on
+// the per-sample path waits for an atomic's return value.
 //
 // Thread mapping: a row of D floats is covered by LPR = min(32, D/4) lanes x VPL
 // float4 each, so a warp handles SPW = 32/LPR samples per pass and every global
 // access of a lane group is one contiguous 16*LPR-byte segment.
 #include "common.cuh"
 
+int brs_assign_slots(const brs_rowset* rs, const long long* const* idx, const long long* n, int n_arrays,
+                     brs_step_ws* ws, cudaStream_t st);
+
 namespace {
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 128;
 constexpr int kWarps = kThreads / 32;
-constexpr int kTile = 128;  // samples per staged index tile
+constexpr int kTile = 64;  // samples per block (one staged index tile)
 
 enum { LOSS_BPR = 0, LOSS_BCE = 1 };
 
@@ -31,12 +41,12 @@ struct MfArgs {
     const float* __restrict__ user_bias;
     const float* __restrict__ item_bias;
     const float* __restrict__ global_bias;
-    float* g_user_emb;
-    float* g_item_emb;
-    float* g_user_bias;
+    float* g_user_emb;   // compact scratch [user capacity, D]
+    float* g_item_emb;   // compact scratch [item capacity, D]
+    float* g_user_bias;  // compact scratch [user capacity]
     float* g_item_bias;
-    brs_rowset user_rows;
-    brs_rowset item_rows;
+    const int* __restrict__ user_slot;  // slot_map of the user rowset (filled by the pre-pass)
+    const int* __restrict__ item_slot;
     brs_step_ws* ws;
     const long long* users;
     const long long* items;  // pos items (bpr) / items (bce)
@@ -54,49 +64,141 @@ struct __align__(16) IdxTile {
     long long c[kTile];  // neg ids, or ratings in the first kTile*4 bytes
 };
 
+__device__ __forceinline__ float4 f4_zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
 __device__ __forceinline__ float4 f4_scale(float s, float4 a) { return make_float4(s * a.x, s * a.y, s * a.z, s * a.w); }
 __device__ __forceinline__ float4 f4_fma(float s, float4 a, float4 b) {
     return make_float4(fmaf(s, a.x, b.x), fmaf(s, a.y, b.y), fmaf(s, a.z, b.z), fmaf(s, a.w, b.w));
 }
 __device__ __forceinline__ float f4_dot(float4 a, float4 b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
 
-// Stage tile `t` of the batch's index lists into `dst`.  TMA path when the slice
-// is a full tile and 16-byte aligned; otherwise (ragged tail / odd views) the
-// block copies it with plain loads and arrives on the same barrier protocol.
-template <int LOSS>
-__device__ __forceinline__ bool stage_tile(const MfArgs& a, long long t, IdxTile* dst, uint64_t* bar) {
-    const long long base = t * kTile;
-    const long long n = min((long long)kTile, a.batch - base);
-    const long long* pa = a.users + base;
-    const long long* pb = a.items + base;
-    const char* pc = (const char*)a.third + base * (LOSS == LOSS_BPR ? 8 : 4);
-    const unsigned bytes_c = (LOSS == LOSS_BPR ? 8u : 4u) * kTile;
-    const bool used_tma = (n == kTile) && ((((uintptr_t)pa | (uintptr_t)pb | (uintptr_t)pc) & 15) == 0);
-    if (used_tma) {
-        if (threadIdx.x == 0) {
-            mbar_expect_tx(bar, 2u * 8u * kTile + bytes_c);
-            tma_load_1d(dst->a, pa, 8u * kTile, bar);
-            tma_load_1d(dst->b, pb, 8u * kTile, bar);
-            tma_load_1d(dst->c, pc, bytes_c, bar);
-        }
-    } else {
-        for (int k = threadIdx.x; k < n; k += kThreads) {
-            dst->a[k] = pa[k];
-            dst->b[k] = pb[k];
-            if (LOSS == LOSS_BPR)
-                dst->c[k] = ((const long long*)pc)[k];
-            else
-                ((float*)dst->c)[k] = ((const float*)pc)[k];
-        }
+// everything one lane holds for one in-flight sample
+template <int VPL, int LOSS>
+struct Sample {
+    long long u, i, j;
+    float rating;
+    bool valid;
+    float4 ue[VPL], ie[VPL], je[VPL];
+    float bu, bi, bj;
+    int su, si, sj;  // gradient-scratch slots
+};
+
+template <int LPR, int VPL, bool FULL, int LOSS>
+__device__ __forceinline__ void sample_load(const MfArgs& a, const IdxTile& T, int s, int tile_n, int gl, int D,
+                                            Sample<VPL, LOSS>& x) {
+    x.valid = s < tile_n;
+    const int sc = x.valid ? s : 0;
+    x.u = T.a[sc];
+    x.i = T.b[sc];
+    x.j = 0;
+    x.rating = 0.f;
+    if (LOSS == LOSS_BPR)
+        x.j = T.c[sc];
+    else
+        x.rating = ((const float*)T.c)[sc];
+    if ((unsigned long long)x.u >= (unsigned long long)a.n_users ||
+        (unsigned long long)x.i >= (unsigned long long)a.n_items ||
+        (unsigned long long)x.j >= (unsigned long long)a.n_items) {
+        x.valid = false;  // flagged by the pre-pass (the reference raises IndexError)
+        x.u = x.i = x.j = 0;
     }
-    return used_tma;
+    const float* ur = a.user_emb + x.u * D;
+    const float* ir = a.item_emb + x.i * D;
+    const float* jr = a.item_emb + x.j * D;
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+        const int col = (v * LPR + gl) * 4;
+        const bool on = FULL || col < D;
+        x.ue[v] = on ? ld_row4(ur + col) : f4_zero();
+        x.ie[v] = on ? ld_row4(ir + col) : f4_zero();
+        if (LOSS == LOSS_BPR) x.je[v] = on ? ld_row4(jr + col) : f4_zero();
+    }
+    x.bu = __ldg(a.user_bias + x.u);
+    x.bi = __ldg(a.item_bias + x.i);
+    x.bj = (LOSS == LOSS_BPR) ? __ldg(a.item_bias + x.j) : 0.f;
+    x.su = __ldg(a.user_slot + x.u);
+    x.si = __ldg(a.item_slot + x.i);
+    x.sj = (LOSS == LOSS_BPR) ? __ldg(a.item_slot + x.j) : 0;
+    if (x.su < 0 || x.si < 0 || x.sj < 0) x.valid = false;  // capacity overflow, flagged by the pre-pass
 }
 
 template <int LPR, int VPL, bool FULL, int LOSS>
-__global__ void __launch_bounds__(kThreads) mf_fwd_bwd_kernel(const MfArgs a) {
+__device__ __forceinline__ void sample_finish(const MfArgs& a, const Sample<VPL, LOSS>& x, int gl, int D, float bg,
+                                              float& loss_acc, float& reg_acc, float& gb_acc) {
+    float dp = 0.f, dn = 0.f, uu = 0.f, ii = 0.f, jj = 0.f;
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+        dp += f4_dot(x.ue[v], x.ie[v]);
+        uu += f4_dot(x.ue[v], x.ue[v]);
+        ii += f4_dot(x.ie[v], x.ie[v]);
+        if (LOSS == LOSS_BPR) {
+            dn += f4_dot(x.ue[v], x.je[v]);
+            jj += f4_dot(x.je[v], x.je[v]);
+        }
+    }
+    dp = group_sum<LPR>(dp);
+    if (LOSS == LOSS_BPR) dn = group_sum<LPR>(dn);
+
+    float cu_i, cu_j = 0.f;  // d loss / d z for the (u,i) and (u,j) scores
+    float loss_k;
+    if (LOSS == LOSS_BPR) {
+        // mf.py:43-48 then torch_engine.py:104-105
+        const float sp = sigmoidf_(dp + x.bu + x.bi + bg);
+        const float sn = sigmoidf_(dn + x.bu + x.bj + bg);
+        const float d = sp - sn;
+        loss_k = -logsigmoidf_(d);
+        const float dx = -a.inv_b / (1.0f + expf(d));  // d/dx of -mean(logsigmoid(x))
+        cu_i = dx * sp * (1.0f - sp);
+        cu_j = -dx * sn * (1.0f - sn);
+    } else {
+        // nn.BCELoss: logs clamped at -100; backward (s-r)/max((1-s)s, 1e-12)/B
+        const float sc_ = sigmoidf_(dp + x.bu + x.bi + bg);
+        loss_k = -(x.rating * fmaxf(logf(sc_), -100.f) + (1.0f - x.rating) * fmaxf(log1pf(-sc_), -100.f));
+        const float ds = (sc_ - x.rating) / fmaxf((1.0f - sc_) * sc_, 1e-12f) * a.inv_b;
+        cu_i = ds * sc_ * (1.0f - sc_);
+    }
+    if (!x.valid) return;
+
+    // regularizer numerator (mf.py:49-54), one forward call per score
+    const float fwd_calls = (LOSS == LOSS_BPR) ? 2.f : 1.f;
+    reg_acc += fwd_calls * uu + ii + jj;
+    if (gl == 0) {
+        reg_acc += fwd_calls * x.bu * x.bu + x.bi * x.bi + x.bj * x.bj;
+        loss_acc += loss_k;
+        gb_acc += cu_i + cu_j;
+    }
+    const float rw = 2.0f * a.reg_w * a.inv_b;  // d(reg_w*regularizer)/d row = rw * row per forward call
+    float* gu = a.g_user_emb + (long long)x.su * D;
+    float* gi = a.g_item_emb + (long long)x.si * D;
+    float* gj = a.g_item_emb + (long long)x.sj * D;
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+        const int col = (v * LPR + gl) * 4;
+        if (FULL || col < D) {
+            float4 du = f4_scale(cu_i, x.ie[v]);
+            if (LOSS == LOSS_BPR) du = f4_fma(cu_j, x.je[v], du);
+            if (a.reg_w != 0.f) du = f4_fma(fwd_calls * rw, x.ue[v], du);
+            red_add4(gu + col, du);
+            float4 di = f4_scale(cu_i, x.ue[v]);
+            if (a.reg_w != 0.f) di = f4_fma(rw, x.ie[v], di);
+            red_add4(gi + col, di);
+            if (LOSS == LOSS_BPR) {
+                float4 dj = f4_scale(cu_j, x.ue[v]);
+                if (a.reg_w != 0.f) dj = f4_fma(rw, x.je[v], dj);
+                red_add4(gj + col, dj);
+            }
+        }
+    }
+    // bias gradients, spread over the first lanes of the group
+    if (gl == 0) red_add1(a.g_user_bias + x.su, cu_i + cu_j + fwd_calls * rw * x.bu);
+    if (gl == 1 % LPR) red_add1(a.g_item_bias + x.si, cu_i + rw * x.bi);
+    if (LOSS == LOSS_BPR && gl == 2 % LPR) red_add1(a.g_item_bias + x.sj, cu_j + rw * x.bj);
+}
+
+template <int LPR, int VPL, bool FULL, int LOSS>
+__global__ void __launch_bounds__(kThreads, (VPL == 1) ? 8 : 4) mf_fwd_bwd_kernel(const MfArgs a) {
     constexpr int SPW = 32 / LPR;
-    __shared__ IdxTile s_tile[2];
-    __shared__ __align__(8) uint64_t s_bar[2];
+    __shared__ IdxTile s_tile;
+    __shared__ __align__(8) uint64_t s_bar;
     __shared__ float s_red[3][kWarps];
 
     const int lane = threadIdx.x & 31;
@@ -104,156 +206,48 @@ __global__ void __launch_bounds__(kThreads) mf_fwd_bwd_kernel(const MfArgs a) {
     const int gl = lane % LPR;   // lane within the row group
     const int grp = lane / LPR;  // which of the warp's SPW samples
     const int D = a.dim;
-    const long long n_tiles = (a.batch + kTile - 1) / kTile;
+    const long long base = (long long)blockIdx.x * kTile;
+    const int tile_n = (int)min((long long)kTile, a.batch - base);
 
-    if (threadIdx.x == 0) {
-        mbar_init(&s_bar[0], 1);
-        mbar_init(&s_bar[1], 1);
-        mbar_fence_init();
+    // ---- stage this block's slice of the index lists: TMA when the slice is a full,
+    //      16-byte aligned tile; plain loads for the ragged tail / odd views ----
+    const long long* pa = a.users + base;
+    const long long* pb = a.items + base;
+    const char* pc = (const char*)a.third + base * (LOSS == LOSS_BPR ? 8 : 4);
+    constexpr unsigned bytes_c = (LOSS == LOSS_BPR ? 8u : 4u) * kTile;
+    const bool use_tma = (tile_n == kTile) && ((((uintptr_t)pa | (uintptr_t)pb | (uintptr_t)pc) & 15) == 0);
+    if (use_tma) {
+        if (threadIdx.x == 0) {
+            mbar_init(&s_bar, 1);
+            mbar_fence_init();
+            mbar_expect_tx(&s_bar, 2u * 8u * kTile + bytes_c);
+            tma_load_1d(s_tile.a, pa, 8u * kTile, &s_bar);
+            tma_load_1d(s_tile.b, pb, 8u * kTile, &s_bar);
+            tma_load_1d(s_tile.c, pc, bytes_c, &s_bar);
+        }
+        __syncthreads();  // barrier object initialised before anyone polls it
+        mbar_wait(&s_bar, 0u);
+    } else {
+        for (int k = threadIdx.x; k < tile_n; k += kThreads) {
+            s_tile.a[k] = pa[k];
+            s_tile.b[k] = pb[k];
+            if (LOSS == LOSS_BPR)
+                s_tile.c[k] = ((const long long*)pc)[k];
+            else
+                ((float*)s_tile.c)[k] = ((const float*)pc)[k];
+        }
+        __syncthreads();
     }
-    __syncthreads();
 
     const float bg = __ldg(a.global_bias);
     float loss_acc = 0.f, reg_acc = 0.f, gb_acc = 0.f;
-    unsigned phase_bits = 0u;  // bit b = parity to wait for on s_bar[b]
-    unsigned tma_bits = 0u;    // bit b = s_tile[b] is being filled by TMA
-
-    long long t = blockIdx.x;
-    int buf = 0;
-    if (t < n_tiles && stage_tile<LOSS>(a, t, &s_tile[0], &s_bar[0])) tma_bits |= 1u;
-
-    for (; t < n_tiles; t += gridDim.x, buf ^= 1) {
-        const long long tn = t + gridDim.x;
-        // prefetch the next tile into the other buffer (its previous readers passed
-        // the __syncthreads at the end of the previous iteration)
-        if (tn < n_tiles) {
-            const bool nt = stage_tile<LOSS>(a, tn, &s_tile[buf ^ 1], &s_bar[buf ^ 1]);
-            tma_bits = (tma_bits & ~(1u << (buf ^ 1))) | ((nt ? 1u : 0u) << (buf ^ 1));
-        }
-        if ((tma_bits >> buf) & 1u) {
-            mbar_wait(&s_bar[buf], (phase_bits >> buf) & 1u);
-            phase_bits ^= 1u << buf;
-        } else {
-            __syncthreads();  // plain-copy path: make the block's stores visible
-        }
-        const IdxTile& T = s_tile[buf];
-        const int tile_n = (int)min((long long)kTile, a.batch - t * kTile);
-
-        for (int base = warp * SPW; base < tile_n; base += kWarps * SPW) {
-            const int s = base + grp;
-            bool valid = s < tile_n;
-            const int sc = valid ? s : tile_n - 1;
-            long long u = T.a[sc], i = T.b[sc];
-            long long j = 0;
-            float rating = 0.f;
-            if (LOSS == LOSS_BPR)
-                j = T.c[sc];
-            else
-                rating = ((const float*)T.c)[sc];
-            if ((unsigned long long)u >= (unsigned long long)a.n_users ||
-                (unsigned long long)i >= (unsigned long long)a.n_items ||
-                (unsigned long long)j >= (unsigned long long)a.n_items) {
-                if (valid && gl == 0) atomicOr(&a.ws->err_flag, 1u);  // reference raises IndexError
-                valid = false;
-                u = i = j = 0;
-            }
-            const float* ur = a.user_emb + u * D;
-            const float* ir = a.item_emb + i * D;
-            const float* jr = a.item_emb + j * D;
-
-            float4 ue[VPL], ie[VPL], je[VPL];
-#pragma unroll
-            for (int v = 0; v < VPL; ++v) {
-                const int col = (v * LPR + gl) * 4;
-                const bool on = FULL || col < D;
-                ue[v] = on ? ld_row4(ur + col) : make_float4(0.f, 0.f, 0.f, 0.f);
-                ie[v] = on ? ld_row4(ir + col) : make_float4(0.f, 0.f, 0.f, 0.f);
-                if (LOSS == LOSS_BPR) je[v] = on ? ld_row4(jr + col) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-            const float bu = __ldg(a.user_bias + u);
-            const float bi = __ldg(a.item_bias + i);
-            const float bj = (LOSS == LOSS_BPR) ? __ldg(a.item_bias + j) : 0.f;
-
-            float dp = 0.f, dn = 0.f, uu = 0.f, ii = 0.f, jj = 0.f;
-#pragma unroll
-            for (int v = 0; v < VPL; ++v) {
-                dp += f4_dot(ue[v], ie[v]);
-                uu += f4_dot(ue[v], ue[v]);
-                ii += f4_dot(ie[v], ie[v]);
-                if (LOSS == LOSS_BPR) {
-                    dn += f4_dot(ue[v], je[v]);
-                    jj += f4_dot(je[v], je[v]);
-                }
-            }
-            dp = group_sum<LPR>(dp);
-            if (LOSS == LOSS_BPR) dn = group_sum<LPR>(dn);
-
-            float cu_i, cu_j = 0.f;  // d loss / d z for the (u,i) and (u,j) scores
-            float loss_k;
-            if (LOSS == LOSS_BPR) {
-                // mf.py:43-48 then torch_engine.py:104-105
-                const float sp = sigmoidf_(dp + bu + bi + bg);
-                const float sn = sigmoidf_(dn + bu + bj + bg);
-                const float x = sp - sn;
-                loss_k = -logsigmoidf_(x);
-                const float dx = -a.inv_b / (1.0f + expf(x));  // d/dx of -mean(logsigmoid(x))
-                cu_i = dx * sp * (1.0f - sp);
-                cu_j = -dx * sn * (1.0f - sn);
-            } else {
-                // nn.BCELoss: logs clamped at -100; backward (s-r)/max((1-s)s, 1e-12)/B
-                const float sc_ = sigmoidf_(dp + bu + bi + bg);
-                loss_k = -(rating * fmaxf(logf(sc_), -100.f) + (1.0f - rating) * fmaxf(log1pf(-sc_), -100.f));
-                const float ds = (sc_ - rating) / fmaxf((1.0f - sc_) * sc_, 1e-12f) * a.inv_b;
-                cu_i = ds * sc_ * (1.0f - sc_);
-            }
-
-            if (valid) {
-                // regularizer numerator (mf.py:49-54), one forward call per score
-                const float fwd_calls = (LOSS == LOSS_BPR) ? 2.f : 1.f;
-                reg_acc += fwd_calls * uu + ii + jj;
-                if (gl == 0) {
-                    reg_acc += fwd_calls * bu * bu + bi * bi + bj * bj;
-                    loss_acc += loss_k;
-                    gb_acc += cu_i + cu_j;
-                }
-                const float rw = 2.0f * a.reg_w * a.inv_b;  // d(reg_w*regularizer)/d row = rw * row per forward call
-                float* gu = a.g_user_emb + u * D;
-                float* gi = a.g_item_emb + i * D;
-                float* gj = a.g_item_emb + j * D;
-#pragma unroll
-                for (int v = 0; v < VPL; ++v) {
-                    const int col = (v * LPR + gl) * 4;
-                    if (FULL || col < D) {
-                        float4 du = f4_scale(cu_i, ie[v]);
-                        if (LOSS == LOSS_BPR) du = f4_fma(cu_j, je[v], du);
-                        if (a.reg_w != 0.f) du = f4_fma(fwd_calls * rw, ue[v], du);
-                        red_add4(gu + col, du);
-                        float4 di = f4_scale(cu_i, ue[v]);
-                        if (a.reg_w != 0.f) di = f4_fma(rw, ie[v], di);
-                        red_add4(gi + col, di);
-                        if (LOSS == LOSS_BPR) {
-                            float4 dj = f4_scale(cu_j, ue[v]);
-                            if (a.reg_w != 0.f) dj = f4_fma(rw, je[v], dj);
-                            red_add4(gj + col, dj);
-                        }
-                    }
-                }
-                // biases + touched-row bookkeeping, spread over the first lanes of the group
-                if (gl == 0) {
-                    red_add1(a.g_user_bias + u, cu_i + cu_j + fwd_calls * rw * bu);
-                    mark_touched(a.user_rows, u);
-                }
-                if (gl == 1 % LPR) {
-                    red_add1(a.g_item_bias + i, cu_i + rw * bi);
-                    mark_touched(a.item_rows, i);
-                }
-                if (LOSS == LOSS_BPR && gl == 2 % LPR) {
-                    red_add1(a.g_item_bias + j, cu_j + rw * bj);
-                    mark_touched(a.item_rows, j);
-                }
-            }
-        }
-        __syncthreads();  // everyone is done with s_tile[buf] before it is refilled
+    // two passes (2*SPW samples) in flight per warp
+    for (int b0 = warp * SPW; b0 < tile_n; b0 += 2 * kWarps * SPW) {
+        Sample<VPL, LOSS> x0, x1;
+        sample_load<LPR, VPL, FULL, LOSS>(a, s_tile, b0 + grp, tile_n, gl, D, x0);
+        sample_load<LPR, VPL, FULL, LOSS>(a, s_tile, b0 + kWarps * SPW + grp, tile_n, gl, D, x1);
+        sample_finish<LPR, VPL, FULL, LOSS>(a, x0, gl, D, bg, loss_acc, reg_acc, gb_acc);
+        sample_finish<LPR, VPL, FULL, LOSS>(a, x1, gl, D, bg, loss_acc, reg_acc, gb_acc);
     }
 
     // block reduction of the scalar outputs -> 3 atomics per block
@@ -266,18 +260,17 @@ __global__ void __launch_bounds__(kThreads) mf_fwd_bwd_kernel(const MfArgs a) {
         s_red[2][warp] = gb_acc;
     }
     __syncthreads();
-    if (warp == 0) {
-        float l = lane < kWarps ? s_red[0][lane] : 0.f;
-        float r = lane < kWarps ? s_red[1][lane] : 0.f;
-        float g = lane < kWarps ? s_red[2][lane] : 0.f;
-        l = warp_sum(l);
-        r = warp_sum(r);
-        g = warp_sum(g);
-        if (lane == 0) {
-            atomicAdd(&a.ws->loss_sum, (double)l);
-            atomicAdd(&a.ws->reg_sum, (double)r);
-            atomicAdd(&a.ws->g_global_bias, g);
+    if (threadIdx.x == 0) {
+        float l = 0.f, r = 0.f, g = 0.f;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) {
+            l += s_red[0][w];
+            r += s_red[1][w];
+            g += s_red[2][w];
         }
+        atomicAdd(&a.ws->loss_sum, (double)l);
+        atomicAdd(&a.ws->reg_sum, (double)r);
+        atomicAdd(&a.ws->g_global_bias, g);
     }
 }
 
@@ -331,10 +324,11 @@ template <int LOSS>
 int launch_fwd_bwd(const MfArgs& a, cudaStream_t st) {
     const int D = a.dim;
     const long long n_tiles = (a.batch + kTile - 1) / kTile;
+    if (n_tiles > 0x7fffffffLL) return BRS_ERR_INVALID_ARG;
 #define BRS_LAUNCH(LPR, VPL, FULL)                                                      \
     do {                                                                                \
         auto k = mf_fwd_bwd_kernel<LPR, VPL, FULL, LOSS>;                               \
-        k<<<grid_for((const void*)k, n_tiles), kThreads, 0, st>>>(a);                   \
+        k<<<(int)n_tiles, kThreads, 0, st>>>(a); /* one tile per block */               \
     } while (0)
     if (D % 4 != 0 || D <= 0 || D > 512) return BRS_ERR_UNSUPPORTED;
     switch (D) {
@@ -389,12 +383,12 @@ int fill_args(const brs_mf_model* m, MfArgs& a, bool need_grad) {
     if (need_grad) {
         if (!a.g_user_emb || !a.g_item_emb || !a.g_user_bias || !a.g_item_bias) return BRS_ERR_INVALID_ARG;
         if ((((uintptr_t)a.g_user_emb | (uintptr_t)a.g_item_emb) & 15) != 0) return BRS_ERR_INVALID_ARG;
-        if (!m->user.rows.bits || !m->user.rows.list || !m->user.rows.count || !m->item.rows.bits ||
+        if (!m->user.rows.slot_map || !m->user.rows.list || !m->user.rows.count || !m->item.rows.slot_map ||
             !m->item.rows.list || !m->item.rows.count)
             return BRS_ERR_INVALID_ARG;
     }
-    a.user_rows = m->user.rows;
-    a.item_rows = m->item.rows;
+    a.user_slot = m->user.rows.slot_map;
+    a.item_slot = m->item.rows.slot_map;
     a.ws = (brs_step_ws*)m->ws;
     a.n_users = m->user.table[0].n_rows;
     a.n_items = m->item.table[0].n_rows;
@@ -418,6 +412,13 @@ int brs_mf_fwd_bwd_impl(const brs_mf_model* model, int loss_kind, const int64_t*
     a.reg_w = reg_weight;
     a.inv_b = 1.0f / (float)batch;
     cudaStream_t st = (cudaStream_t)stream;
+    {   // pre-pass: range-check the indices and give every touched row a slot in the compact scratch
+        const brs_rowset rs[3] = {model->user.rows, model->item.rows, model->item.rows};
+        const long long* idx[3] = {(const long long*)users, (const long long*)items, (const long long*)third};
+        const long long n[3] = {batch, batch, batch};
+        rc = brs_assign_slots(rs, idx, n, loss_kind == LOSS_BPR ? 3 : 2, a.ws, st);
+        if (rc != BRS_OK) return rc;
+    }
     if (loss_kind == LOSS_BPR) return launch_fwd_bwd<LOSS_BPR>(a, st);
     if (loss_kind == LOSS_BCE) return launch_fwd_bwd<LOSS_BCE>(a, st);
     return BRS_ERR_INVALID_ARG;

@@ -1,16 +1,21 @@
-// optimizer.step() for embedding tables -- sm_100a.
+// Touched-row bookkeeping and optimizer.step() for embedding tables -- sm_100a.
 //
 // Replaces torch.optim.{SGD,Adam,RMSprop}.step over dense [N,D] gradients
 // (beta_rec/models/torch_engine.py:23-39, called at beta_rec/models/mf.py:118).
 //
-//  * rows kernels: a warp per TOUCHED row (list built by the fwd/bwd kernel):
-//    read grad row + weight row (+ m, v), update, write back, zero the grad row,
-//    clear the touched bit.  Exact for SGD (g = 0 elsewhere => no change).
-//  * dense sweep: every element of every table, g = 0 for untouched rows --
-//    what the reference's dense Adam/RMSprop actually does each step.
-// The last block to finish also applies the dense parameters (global bias),
-// publishes {loss, regularizer} and resets the step scratch.
+//  * assign_slots: one thread per batch index; the first toucher of a row claims the
+//    next slot of the entity's compact gradient scratch (slot_map / list / count).
+//  * rows kernels: a warp per group of TOUCHED rows (4 rows in flight per warp): read
+//    the scratch row + weight row (+ m, v), update, write back, zero the scratch row,
+//    release the slot.  Exact for SGD (g = 0 elsewhere => no change).
+//  * dense sweep: every element of every table, g = 0 for untouched rows -- what the
+//    reference's dense Adam/RMSprop actually does each step.
+// The last block to finish also applies the ws-sourced scalar (MF global bias),
+// publishes {loss, regularizer, status} and resets the step scratch.
 #include "common.cuh"
+
+int brs_assign_slots(const brs_rowset* rs, const long long* const* idx, const long long* n, int n_arrays,
+                     brs_step_ws* ws, cudaStream_t st);
 
 namespace {
 
@@ -18,7 +23,37 @@ constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 constexpr int kMaxEntities = 4;
 constexpr int kMaxDense = 16;
+constexpr int kMaxAssign = 4;
 
+// ---------------------------------------------------------------------------
+// slot assignment pre-pass
+// ---------------------------------------------------------------------------
+struct AssignArgs {
+    brs_rowset rs[kMaxAssign];
+    const long long* idx[kMaxAssign];
+    long long n[kMaxAssign];
+    long long offset[kMaxAssign + 1];
+    int n_arrays;
+    unsigned int* err_flag;
+};
+
+__global__ void __launch_bounds__(kThreads) assign_slots_kernel(const AssignArgs a) {
+    const long long total = a.offset[a.n_arrays];
+    for (long long t = (long long)blockIdx.x * kThreads + threadIdx.x; t < total; t += (long long)gridDim.x * kThreads) {
+        int k = 0;
+        while (k + 1 < a.n_arrays && t >= a.offset[k + 1]) ++k;
+        const long long row = a.idx[k][t - a.offset[k]];
+        if ((unsigned long long)row >= (unsigned long long)a.rs[k].n_rows) {
+            atomicOr(a.err_flag, 1u);  // the reference raises IndexError (nn.Embedding)
+            continue;
+        }
+        claim_slot(a.rs[k], row, a.err_flag);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// optimizer math
+// ---------------------------------------------------------------------------
 struct OptScalars {  // per-step scalars, computed in double like torch does on the host
     float lr;
     float one_minus_b1, b2, one_minus_b2;
@@ -65,6 +100,14 @@ __device__ __forceinline__ void opt_elem(float& p, float g, float& m, float& v, 
     }
 }
 
+template <int KIND>
+__device__ __forceinline__ void opt_elem4(float4& p, const float4& g, float4& m, float4& v, const OptScalars& s) {
+    opt_elem<KIND>(p.x, g.x, m.x, v.x, s);
+    opt_elem<KIND>(p.y, g.y, m.y, v.y, s);
+    opt_elem<KIND>(p.z, g.z, m.z, v.z, s);
+    opt_elem<KIND>(p.w, g.w, m.w, v.w, s);
+}
+
 struct ApplyArgs {
     brs_entity ent[kMaxEntities];
     int n_ent;
@@ -79,11 +122,13 @@ struct ApplyArgs {
     int advance_step;   // last block: ws->step += 1, reset sums
 };
 
+// one touched row of one table: scratch row `slot` -> weight row `row`
 template <int KIND>
-__device__ __forceinline__ void update_row(const brs_table& tb, long long row, int lane, const OptScalars& s) {
+__device__ __forceinline__ void update_row(const brs_table& tb, long long row, long long slot, int lane,
+                                           const OptScalars& s) {
     const int d = tb.dim;
     float* w = tb.weight + row * d;
-    float* g = tb.grad + row * d;
+    float* g = tb.grad + slot * d;
     float* m = (KIND == BRS_ADAM) ? tb.m + row * d : nullptr;
     float* v = (KIND != BRS_SGD) ? tb.v + row * d : nullptr;
     if ((d & 3) == 0) {
@@ -93,10 +138,7 @@ __device__ __forceinline__ void update_row(const brs_table& tb, long long row, i
             float4 mv = make_float4(0.f, 0.f, 0.f, 0.f), vv = mv;
             if (KIND == BRS_ADAM) mv = *(const float4*)(m + c);
             if (KIND != BRS_SGD) vv = *(const float4*)(v + c);
-            opt_elem<KIND>(wv.x, gv.x, mv.x, vv.x, s);
-            opt_elem<KIND>(wv.y, gv.y, mv.y, vv.y, s);
-            opt_elem<KIND>(wv.z, gv.z, mv.z, vv.z, s);
-            opt_elem<KIND>(wv.w, gv.w, mv.w, vv.w, s);
+            opt_elem4<KIND>(wv, gv, mv, vv, s);
             *(float4*)(w + c) = wv;
             if (KIND == BRS_ADAM) *(float4*)(m + c) = mv;
             if (KIND != BRS_SGD) *(float4*)(v + c) = vv;
@@ -116,17 +158,45 @@ __device__ __forceinline__ void update_row(const brs_table& tb, long long row, i
     }
 }
 
-// dense parameters + publication of the step's scalars; run by the LAST block only
+// fast path: ROWS touched rows of a dim <= 128 (dim % 4 == 0) table in flight per warp
+template <int KIND, int ROWS>
+__device__ __forceinline__ void update_rows_small(const brs_table& tb, const long long* row, const long long* slot,
+                                                  int n, int lane, const OptScalars& s) {
+    const int d = tb.dim, c = lane * 4;
+    if (c >= d) return;
+    float4 gv[ROWS], wv[ROWS], mv[ROWS], vv[ROWS];
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+        mv[r] = vv[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < n) {
+            gv[r] = *(const float4*)(tb.grad + slot[r] * d + c);
+            wv[r] = *(const float4*)(tb.weight + row[r] * d + c);
+            if (KIND == BRS_ADAM) mv[r] = *(const float4*)(tb.m + row[r] * d + c);
+            if (KIND != BRS_SGD) vv[r] = *(const float4*)(tb.v + row[r] * d + c);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+        if (r < n) {
+            opt_elem4<KIND>(wv[r], gv[r], mv[r], vv[r], s);
+            *(float4*)(tb.weight + row[r] * d + c) = wv[r];
+            if (KIND == BRS_ADAM) *(float4*)(tb.m + row[r] * d + c) = mv[r];
+            if (KIND != BRS_SGD) *(float4*)(tb.v + row[r] * d + c) = vv[r];
+            *(float4*)(tb.grad + slot[r] * d + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+}
+
+// dense (Linear / bias) parameters whose gradients were completed by earlier kernels:
+// element-wise over the whole grid; their grads are cleared for the next step
 template <int KIND>
-__device__ void finalize(const ApplyArgs& a, const OptScalars& s) {
-    for (int k = 0; k < a.n_dense; ++k) {
+__device__ __forceinline__ void dense_params_update(const ApplyArgs& a, const OptScalars& s) {
+    const long long tid = (long long)blockIdx.x * kThreads + threadIdx.x;
+    const long long nthreads = (long long)gridDim.x * kThreads;
+    for (int k = (a.dense_grad_from_ws ? 1 : 0); k < a.n_dense; ++k) {
         const brs_dense_param& dp = a.dense[k];
-        for (long long e = threadIdx.x; e < dp.numel; e += kThreads) {
-            float g;
-            if (k == 0 && a.dense_grad_from_ws)
-                g = a.ws->g_global_bias;
-            else
-                g = dp.grad[e];
+        for (long long e = tid; e < dp.numel; e += nthreads) {
+            const float g = dp.grad[e];
             float w = dp.weight[e];
             float m = (KIND == BRS_ADAM) ? dp.m[e] : 0.f;
             float v = (KIND != BRS_SGD) ? dp.v[e] : 0.f;
@@ -134,15 +204,32 @@ __device__ void finalize(const ApplyArgs& a, const OptScalars& s) {
             dp.weight[e] = w;
             if (KIND == BRS_ADAM) dp.m[e] = m;
             if (KIND != BRS_SGD) dp.v[e] = v;
-            if (!(k == 0 && a.dense_grad_from_ws) && dp.grad) dp.grad[e] = 0.f;
+            dp.grad[e] = 0.f;
         }
+    }
+}
+
+// the ws-sourced scalar parameter (MF global bias) + publication of the step's scalars;
+// run by the LAST block only (every other block has finished reading ws by then)
+template <int KIND>
+__device__ void finalize(const ApplyArgs& a, const OptScalars& s) {
+    if (a.dense_grad_from_ws && a.n_dense > 0 && threadIdx.x == 0) {
+        const brs_dense_param& dp = a.dense[0];
+        const float g = a.ws->g_global_bias;
+        float w = dp.weight[0];
+        float m = (KIND == BRS_ADAM) ? dp.m[0] : 0.f;
+        float v = (KIND != BRS_SGD) ? dp.v[0] : 0.f;
+        opt_elem<KIND>(w, g, m, v, s);
+        dp.weight[0] = w;
+        if (KIND == BRS_ADAM) dp.m[0] = m;
+        if (KIND != BRS_SGD) dp.v[0] = v;
     }
     __syncthreads();
     if (threadIdx.x == 0 && a.ws) {
         if (a.out) {  // brs_step_out
             a.out[0] = (float)(a.ws->loss_sum * a.inv_batch);
             a.out[1] = (float)(a.ws->reg_sum * a.inv_batch);
-            a.out[2] = (float)a.ws->err_flag;  // 0 ok | 1 index out of range | 2 touched-list overflow
+            a.out[2] = (float)a.ws->err_flag;  // 0 ok | 1 index out of range | 2 touched-row capacity overflow
             a.out[3] = 0.f;
         }
         if (a.advance_step) {
@@ -156,7 +243,6 @@ __device__ void finalize(const ApplyArgs& a, const OptScalars& s) {
     }
 }
 
-template <int KIND>
 __device__ __forceinline__ bool last_block(const ApplyArgs& a) {
     __shared__ bool s_last;
     __threadfence();
@@ -170,9 +256,15 @@ __device__ __forceinline__ bool last_block(const ApplyArgs& a) {
     return s_last;
 }
 
+__device__ __forceinline__ int clamped_count(const brs_rowset& rs) {
+    const int c = *rs.count;
+    return c < rs.capacity ? c : rs.capacity;
+}
+
 // ---- touched rows only ------------------------------------------------------
 template <int KIND>
 __global__ void __launch_bounds__(kThreads) rows_apply_kernel(const ApplyArgs a) {
+    constexpr int ROWS = 4;
     __shared__ OptScalars s_opt;
     __shared__ int s_cnt[kMaxEntities + 1];
     if (threadIdx.x == 0) {
@@ -181,12 +273,7 @@ __global__ void __launch_bounds__(kThreads) rows_apply_kernel(const ApplyArgs a)
         int acc = 0;
         for (int e = 0; e < a.n_ent; ++e) {
             s_cnt[e] = acc;
-            int c = *a.ent[e].rows.count;
-            if (c > a.ent[e].rows.capacity) {  // list too small for this batch: rows would be lost
-                c = a.ent[e].rows.capacity;
-                if (a.ws) atomicOr(&a.ws->err_flag, 2u);
-            }
-            acc += c;
+            acc += (clamped_count(a.ent[e].rows) + ROWS - 1) / ROWS;  // work items = groups of ROWS slots
         }
         s_cnt[a.n_ent] = acc;
     }
@@ -198,25 +285,45 @@ __global__ void __launch_bounds__(kThreads) rows_apply_kernel(const ApplyArgs a)
         int e = 0;
         while (e + 1 < a.n_ent && r >= s_cnt[e + 1]) ++e;
         const brs_entity& en = a.ent[e];
-        const long long row = en.rows.list[r - s_cnt[e]];
-        for (int k = 0; k < en.n_tables; ++k) update_row<KIND>(en.table[k], row, lane, s);
-        if (lane == 0) atomicAnd(en.rows.bits + (row >> 5), ~(1u << (row & 31)));
+        const int cnt = clamped_count(en.rows);
+        const int s0 = (r - s_cnt[e]) * ROWS;
+        const int n = min(ROWS, cnt - s0);
+        long long row[ROWS], slot[ROWS];
+#pragma unroll
+        for (int k = 0; k < ROWS; ++k) {
+            slot[k] = s0 + k;
+            row[k] = (k < n) ? en.rows.list[s0 + k] : 0;
+        }
+        for (int k = 0; k < en.n_tables; ++k) {
+            const brs_table& tb = en.table[k];
+            if ((tb.dim & 3) == 0 && tb.dim <= 128) {
+                update_rows_small<KIND, ROWS>(tb, row, slot, n, lane, s);
+            } else if (tb.dim == 1) {  // bias tables: one lane per row
+#pragma unroll
+                for (int q = 0; q < ROWS; ++q)
+                    if (lane == q && q < n) update_row<KIND>(tb, row[q], slot[q], 0, s);
+            } else {
+                for (int q = 0; q < n; ++q) update_row<KIND>(tb, row[q], slot[q], lane, s);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < ROWS; ++q)
+            if (lane == q && q < n) en.rows.slot_map[row[q]] = BRS_SLOT_NONE;  // release the slot
     }
+    dense_params_update<KIND>(a, s);
     if (a.ws) {
-        if (last_block<KIND>(a)) {
+        if (last_block(a)) {
             if (threadIdx.x < a.n_ent) *a.ent[threadIdx.x].rows.count = 0;
             finalize<KIND>(a, s);
         }
-    } else if (blockIdx.x == 0 && a.n_dense) {
-        finalize<KIND>(a, s);
     }
 }
 
 // ---- every row (reference-exact Adam / RMSprop) -----------------------------
 // grid-stride over float4 vectors (or scalars when dim % 4 != 0) of one table
 template <int KIND>
-__device__ __forceinline__ void sweep_table(const brs_table& tb, const unsigned int* __restrict__ bits,
-                                            const OptScalars& s, long long tid, long long nthreads) {
+__device__ __forceinline__ void sweep_table(const brs_table& tb, const int* __restrict__ slot_map, const OptScalars& s,
+                                            long long tid, long long nthreads) {
     const int d = tb.dim;
     if ((d & 3) == 0) {
         const int vpr = d >> 2;
@@ -224,20 +331,18 @@ __device__ __forceinline__ void sweep_table(const brs_table& tb, const unsigned 
         const int shift = (vpr & (vpr - 1)) == 0 ? __ffs(vpr) - 1 : -1;
         for (long long i = tid; i < nvec; i += nthreads) {
             const long long row = shift >= 0 ? (i >> shift) : (nvec < (1ll << 31) ? (long long)((unsigned)i / (unsigned)vpr) : i / vpr);
-            const bool touched = (bits[row >> 5] >> (row & 31)) & 1u;
+            const int slot = slot_map[row];
             float4 gv = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (touched) {
-                gv = ((const float4*)tb.grad)[i];
-                ((float4*)tb.grad)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (slot >= 0) {
+                float4* gp = (float4*)(tb.grad + (long long)slot * d) + (i - row * vpr);
+                gv = *gp;
+                *gp = make_float4(0.f, 0.f, 0.f, 0.f);
             }
             float4 wv = ((const float4*)tb.weight)[i];
             float4 mv = make_float4(0.f, 0.f, 0.f, 0.f), vv = mv;
             if (KIND == BRS_ADAM) mv = ((const float4*)tb.m)[i];
             if (KIND != BRS_SGD) vv = ((const float4*)tb.v)[i];
-            opt_elem<KIND>(wv.x, gv.x, mv.x, vv.x, s);
-            opt_elem<KIND>(wv.y, gv.y, mv.y, vv.y, s);
-            opt_elem<KIND>(wv.z, gv.z, mv.z, vv.z, s);
-            opt_elem<KIND>(wv.w, gv.w, mv.w, vv.w, s);
+            opt_elem4<KIND>(wv, gv, mv, vv, s);
             ((float4*)tb.weight)[i] = wv;
             if (KIND == BRS_ADAM) ((float4*)tb.m)[i] = mv;
             if (KIND != BRS_SGD) ((float4*)tb.v)[i] = vv;
@@ -246,11 +351,12 @@ __device__ __forceinline__ void sweep_table(const brs_table& tb, const unsigned 
         const long long n = tb.n_rows * d;
         for (long long i = tid; i < n; i += nthreads) {
             const long long row = i / d;
-            const bool touched = (bits[row >> 5] >> (row & 31)) & 1u;
+            const int slot = slot_map[row];
             float g = 0.f;
-            if (touched) {
-                g = tb.grad[i];
-                tb.grad[i] = 0.f;
+            if (slot >= 0) {
+                float* gp = tb.grad + (long long)slot * d + (i - row * d);
+                g = *gp;
+                *gp = 0.f;
             }
             float w = tb.weight[i];
             float m = (KIND == BRS_ADAM) ? tb.m[i] : 0.f;
@@ -272,24 +378,21 @@ __global__ void __launch_bounds__(kThreads) dense_sweep_kernel(const ApplyArgs a
     const long long tid = (long long)blockIdx.x * kThreads + threadIdx.x;
     const long long nthreads = (long long)gridDim.x * kThreads;
     for (int e = 0; e < a.n_ent; ++e)
-        for (int k = 0; k < a.ent[e].n_tables; ++k) sweep_table<KIND>(a.ent[e].table[k], a.ent[e].rows.bits, s, tid, nthreads);
+        for (int k = 0; k < a.ent[e].n_tables; ++k)
+            sweep_table<KIND>(a.ent[e].table[k], a.ent[e].rows.slot_map, s, tid, nthreads);
+    dense_params_update<KIND>(a, s);
     if (a.ws) {
-        if (last_block<KIND>(a)) finalize<KIND>(a, s);
-    } else if (blockIdx.x == 0 && a.n_dense) {
-        finalize<KIND>(a, s);
+        if (last_block(a)) finalize<KIND>(a, s);
     }
 }
 
-// clears the touched bits after a dense sweep (the sweep itself reads them)
+// releases the slots after a dense sweep (the sweep itself reads the slot maps)
 __global__ void __launch_bounds__(kThreads) rowset_clear_kernel(const ApplyArgs a) {
     for (int e = 0; e < a.n_ent; ++e) {
         const brs_rowset& rs = a.ent[e].rows;
-        int c = *rs.count;
-        if (c > rs.capacity) c = rs.capacity;
-        for (int r = blockIdx.x * kThreads + threadIdx.x; r < c; r += gridDim.x * kThreads) {
-            const long long row = rs.list[r];
-            atomicAnd(rs.bits + (row >> 5), ~(1u << (row & 31)));
-        }
+        const int c = clamped_count(rs);
+        for (int r = blockIdx.x * kThreads + threadIdx.x; r < c; r += gridDim.x * kThreads)
+            rs.slot_map[rs.list[r]] = BRS_SLOT_NONE;
     }
 }
 
@@ -302,7 +405,7 @@ int validate_entities(const brs_entity* ents, int n, int kind) {
     for (int e = 0; e < n; ++e) {
         const brs_entity& en = ents[e];
         if (en.n_tables < 0 || en.n_tables > BRS_MAX_ENTITY_TABLES) return BRS_ERR_INVALID_ARG;
-        if (!en.rows.bits || !en.rows.list || !en.rows.count) return BRS_ERR_INVALID_ARG;
+        if (!en.rows.slot_map || !en.rows.list || !en.rows.count || en.rows.capacity <= 0) return BRS_ERR_INVALID_ARG;
         for (int k = 0; k < en.n_tables; ++k) {
             const brs_table& t = en.table[k];
             if (!t.weight || !t.grad || t.dim <= 0 || t.n_rows < 0) return BRS_ERR_INVALID_ARG;
@@ -352,16 +455,91 @@ int launch_apply(const ApplyArgs& a, int mode, long long max_rows_hint, cudaStre
     } else {
         auto k = rows_apply_kernel<KIND>;
         int grid = persistent_grid((const void*)k);
-        long long need = (max_rows_hint + kWarps - 1) / kWarps;
+        long long need = (max_rows_hint / 4 + kWarps) / kWarps;  // 4 rows per warp work item
+        for (int d = 0; d < a.n_dense; ++d) need = max(need, (long long)((a.dense[d].numel + kThreads - 1) / kThreads));
         if (need < 1) need = 1;
         if (grid > need) grid = (int)need;
         k<<<grid, kThreads, 0, st>>>(a);
+        if (!a.ws) rowset_reset_counts_kernel<<<1, 32, 0, st>>>(a);  // stand-alone use: no last-block finalize
     }
     BRS_CUDA_CHECK(cudaGetLastError());
     return BRS_OK;
 }
 
+// grad_scratch[slot_map[idx[k]]] += scale * src[k]: the scatter half of an embedding backward
+__global__ void __launch_bounds__(kThreads) rows_scatter_grad_kernel(brs_table tb, const int* __restrict__ slot_map,
+                                                                     const long long* __restrict__ idx, long long n,
+                                                                     const float* __restrict__ src, float scale) {
+    const int lane = threadIdx.x & 31;
+    const int d = tb.dim;
+    for (long long k = (long long)blockIdx.x * kWarps + (threadIdx.x >> 5); k < n; k += (long long)gridDim.x * kWarps) {
+        const long long row = idx[k];
+        if ((unsigned long long)row >= (unsigned long long)tb.n_rows) continue;
+        const long long slot = slot_map[row];
+        if (slot < 0) continue;
+        float* g = tb.grad + slot * d;
+        const float* sp = src + k * d;
+        if ((d & 3) == 0) {
+            for (int c = lane * 4; c < d; c += 128) {
+                const float4 x = *(const float4*)(sp + c);
+                red_add4(g + c, make_float4(scale * x.x, scale * x.y, scale * x.z, scale * x.w));
+            }
+        } else {
+            for (int c = lane; c < d; c += 32) red_add1(g + c, scale * sp[c]);
+        }
+    }
+}
+
 }  // namespace
+
+extern "C" int brs_rows_assign(const brs_rowset* rows, const int64_t* idx, int64_t n, void* ws, void* stream) {
+    if (!rows || !ws) return BRS_ERR_INVALID_ARG;
+    const long long* ip = (const long long*)idx;
+    const long long nn = n;
+    return brs_assign_slots(rows, &ip, &nn, 1, (brs_step_ws*)ws, (cudaStream_t)stream);
+}
+
+extern "C" int brs_rows_scatter_grad(const brs_entity* entity, int32_t table, const int64_t* idx, int64_t n,
+                                     const float* src, float scale, void* stream) {
+    if (!entity || table < 0 || table >= entity->n_tables || !idx || !src || n < 0) return BRS_ERR_INVALID_ARG;
+    const brs_table& tb = entity->table[table];
+    if (!tb.grad || !entity->rows.slot_map) return BRS_ERR_INVALID_ARG;
+    if (n == 0) return BRS_OK;
+    long long blocks = (n + kWarps - 1) / kWarps;
+    const long long cap = (long long)brs_sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    rows_scatter_grad_kernel<<<(int)blocks, kThreads, 0, (cudaStream_t)stream>>>(tb, entity->rows.slot_map,
+                                                                                 (const long long*)idx, n, src, scale);
+    BRS_CUDA_CHECK(cudaGetLastError());
+    return BRS_OK;
+}
+
+// range-check the index arrays and give every touched row a slot (shared with the model kernels)
+int brs_assign_slots(const brs_rowset* rs, const long long* const* idx, const long long* n, int n_arrays,
+                     brs_step_ws* ws, cudaStream_t st) {
+    if (n_arrays < 1 || n_arrays > kMaxAssign || !ws) return BRS_ERR_INVALID_ARG;
+    AssignArgs a;
+    memset(&a, 0, sizeof(a));
+    long long off = 0;
+    for (int k = 0; k < n_arrays; ++k) {
+        if (!rs[k].slot_map || !rs[k].list || !rs[k].count || !idx[k] || n[k] < 0) return BRS_ERR_INVALID_ARG;
+        a.rs[k] = rs[k];
+        a.idx[k] = idx[k];
+        a.n[k] = n[k];
+        a.offset[k] = off;
+        off += n[k];
+    }
+    a.offset[n_arrays] = off;
+    a.n_arrays = n_arrays;
+    a.err_flag = &ws->err_flag;
+    if (off == 0) return BRS_OK;
+    long long blocks = (off + kThreads - 1) / kThreads;
+    const long long cap = (long long)brs_sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    assign_slots_kernel<<<(int)blocks, kThreads, 0, st>>>(a);
+    BRS_CUDA_CHECK(cudaGetLastError());
+    return BRS_OK;
+}
 
 // shared with abi.cu: apply `opt` to entities + dense params (+ finalize through ws)
 int brs_apply_impl(const brs_entity* ents, int n_ent, const brs_dense_param* dense, int n_dense,

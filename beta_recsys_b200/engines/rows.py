@@ -14,19 +14,25 @@ class EntityState(object):
         self.names = [n for n, _ in tables]
         self.weights = [w for _, w in tables]
         self.capacity = int(max(1, min(self.n_rows, capacity)))
-        self.bits = torch.zeros((self.n_rows + 31) // 32, dtype=torch.int32, device=device)
-        self.list = torch.zeros(self.capacity, dtype=torch.int32, device=device)
+        self.slot_map = torch.full((self.n_rows,), -1, dtype=torch.int32, device=device)
         self.count = torch.zeros(1, dtype=torch.int32, device=device)
-        self.grads, self.states = [], []
+        self.states = []
         for name, w in tables:
             assert w.is_cuda and w.dtype == torch.float32 and w.is_contiguous() and w.shape[0] == self.n_rows
-            self.grads.append(torch.zeros_like(w))
             self.states.append(optimizer.add_param(name, w))
+        self._alloc_scratch()
         self.struct = self._make_struct()
+
+    def _alloc_scratch(self):
+        """Compact gradient scratch [capacity, dim] per table + the slot list: the only
+        per-step gradient storage (the reference materialises table-sized dense grads)."""
+        dev = self.slot_map.device
+        self.list = torch.zeros(self.capacity, dtype=torch.int32, device=dev)
+        self.grads = [torch.zeros((self.capacity, w.shape[1]), dtype=torch.float32, device=dev) for w in self.weights]
 
     def _make_struct(self):
         e = _lib.Entity()
-        e.rows = _lib.Rowset(_lib.ptr(self.bits), _lib.ptr(self.list), _lib.ptr(self.count), self.n_rows,
+        e.rows = _lib.Rowset(_lib.ptr(self.slot_map), _lib.ptr(self.list), _lib.ptr(self.count), self.n_rows,
                              self.capacity, 0)
         e.n_tables = len(self.weights)
         for k, (w, g, st) in enumerate(zip(self.weights, self.grads, self.states)):
@@ -39,7 +45,7 @@ class EntityState(object):
         capacity = int(max(1, min(self.n_rows, capacity)))
         if capacity > self.capacity:
             self.capacity = capacity
-            self.list = torch.zeros(capacity, dtype=torch.int32, device=self.list.device)
+            self._alloc_scratch()  # between steps the scratch is all-zero, so nothing to carry over
             self.struct = self._make_struct()
             return True
         return False

@@ -66,7 +66,10 @@ typedef struct brs_opt {
 /* ---- one embedding table + its per-step gradient scratch and optimizer state ---- */
 typedef struct brs_table {
     float *weight;   /* [n_rows, dim] row-major; 16-byte aligned when dim % 4 == 0 */
-    float *grad;     /* [n_rows, dim] gradient accumulator; all-zero between steps */
+    float *grad;     /* [rowset.capacity, dim] COMPACT gradient scratch: row s holds the summed gradient of
+                        table row rowset.list[s]; all-zero between steps.  The same few tens of MB are
+                        reused every step, so the scatter-add stays in L2 instead of touching a
+                        table-sized dense gradient (what autograd materialises in the reference). */
     float *m;        /* Adam exp_avg            (NULL for SGD / RMSprop) */
     float *v;        /* Adam exp_avg_sq / RMSprop square_avg (NULL for SGD) */
     int64_t n_rows;
@@ -76,11 +79,11 @@ typedef struct brs_table {
 
 /* ---- rows of one entity (users or items) touched by the current step ---- */
 typedef struct brs_rowset {
-    uint32_t *bits;  /* [(n_rows+31)/32] touched bitmap; all-zero between steps */
-    int32_t *list;   /* [capacity] touched row ids, unordered */
-    int32_t *count;  /* [1] number of valid entries in list; zero between steps */
+    int32_t *slot_map; /* [n_rows] slot of the row in list/grad scratch, -1 when untouched; all -1 between steps */
+    int32_t *list;     /* [capacity] touched row ids in slot order */
+    int32_t *count;    /* [1] number of valid entries in list; zero between steps */
     int64_t n_rows;
-    int32_t capacity; /* >= min(n_rows, occurrences per batch) */
+    int32_t capacity;  /* >= min(n_rows, occurrences per batch) */
     int32_t pad_;
 } brs_rowset;
 
@@ -164,7 +167,65 @@ int brs_mf_train_batches(const brs_mf_model *model, const brs_opt *opt, int32_t 
 int brs_mf_predict(const brs_mf_model *model, const int64_t *users, const int64_t *items, int64_t n,
                    float *scores, void *stream);
 
-/* ---- generic row optimizers on entities (K6 in SURVEY.md section 2b) ---- */
+/* ---- NCF family: beta_rec/models/{gmf,mlp,ncf}.py ---- */
+#define BRS_NCF_GMF 0    /* GMF  : sigmoid(w.(u*i)+b)                                   gmf.py:29-36  */
+#define BRS_NCF_MLP 1    /* MLP  : cat -> [Linear,ReLU]xn -> Linear -> sigmoid          mlp.py:40-51  */
+#define BRS_NCF_NEUMF 2  /* NeuMF: relu(cat) -> [Linear,ReLU]xn ; cat with u_mf*i_mf -> Linear -> sigmoid  ncf.py:52-71 */
+#define BRS_NCF_MAX_LAYERS 6
+
+typedef struct brs_ncf_model {
+    int32_t kind;      /* BRS_NCF_* */
+    int32_t n_layers;  /* config["model"]["mlp_config"]["n_layers"]; 0 for GMF */
+    int32_t emb_dim;   /* config["model"]["emb_dim"]: GMF / MF-part width and tower output width */
+    int32_t mlp_dim;   /* emb_dim * 2^(n_layers-1): width of the MLP-side embedding rows; 0 for GMF */
+    brs_entity user;   /* NeuMF: table[0] = embedding_user_mlp [U,mlp_dim], table[1] = embedding_user_mf [U,emb_dim];
+                          MLP / GMF: table[0] = embedding_user */
+    brs_entity item;   /* same for items */
+    brs_dense_param fc_weight[BRS_NCF_MAX_LAYERS]; /* fc_layers.{3l+1}.weight [in_l/2, in_l], in_l = 2*mlp_dim >> l */
+    brs_dense_param fc_bias[BRS_NCF_MAX_LAYERS];
+    brs_dense_param out_weight;                    /* affine_output.weight [1, emb_dim (GMF, MLP) | 2*emb_dim (NeuMF)] */
+    brs_dense_param out_bias;                      /* affine_output.bias [1] */
+    float *act[BRS_NCF_MAX_LAYERS + 1];   /* act[0] = tower input [max_batch, 2*mlp_dim], act[l] = output of layer l */
+    float *dact[BRS_NCF_MAX_LAYERS + 1];  /* gradients of the same shapes */
+    float *mfv;                           /* [max_batch, emb_dim] u_mf * i_mf (NeuMF) */
+    float *dz;                            /* [max_batch] d loss / d logit */
+    int64_t max_batch;
+    void *ws;                             /* BRS_STEP_WS_BYTES */
+} brs_ncf_model;
+
+/* forward + BCELoss + backward of one batch: gradients of the embedding rows go to table.grad
+ * (touched rows recorded), gradients of the Linear layers to their brs_dense_param.grad
+ * (replaces NeuMF.forward / GMF.forward / MLP.forward + nn.BCELoss + loss.backward():
+ * ncf.py:109-117, gmf.py:69-77, mlp.py:87-95) */
+int brs_ncf_fwd_bwd(const brs_ncf_model *model, const int64_t *users, const int64_t *items, const float *ratings,
+                    int64_t batch, void *stream);
+/* optimizer.step() over the embedding tables and the Linear parameters + loss.item() (ncf.py:118-119) */
+int brs_ncf_apply(const brs_ncf_model *model, const brs_opt *opt, int64_t batch, float *out /* brs_step_out */,
+                  void *stream);
+/* NeuMF.predict / GMF.predict / MLP.predict (ncf.py:73-78): sigmoid scores, chunked by max_batch */
+int brs_ncf_predict(const brs_ncf_model *model, const int64_t *users, const int64_t *items, int64_t n, float *scores,
+                    void *stream);
+/* train_an_epoch's inner loop (ncf.py:132-138) over (user,item,rating) arrays resident in HBM */
+int brs_ncf_train_batches(const brs_ncf_model *model, const brs_opt *opt, const int64_t *users, const int64_t *items,
+                          const float *ratings, int64_t n, int64_t batch, float *out /* brs_step_out[] */,
+                          void *stream);
+
+/* the Linear building blocks of the tower (nn.Linear forward / backward), row-major fp32:
+ *   fwd: y[m,n] = (relu)(x[m,k] . w[n,k]^T + b[n])
+ *   bwd: dw[n,k] += dy^T x ; db[n] += colsum(dy) (db may be NULL);
+ *        dx[m,k] = (dy . w) * (relu_mask_src[m,k] > 0)   (dx may be NULL; mask source may be NULL) */
+int brs_mlp_fwd(const float *x, const float *w, const float *b, float *y, int64_t m, int32_t n, int32_t k,
+                int32_t relu, void *stream);
+int brs_mlp_bwd(const float *dy, const float *x, const float *w, float *dx, float *dw, float *db,
+                const float *relu_mask_src, int64_t m, int32_t n, int32_t k, void *stream);
+
+/* ---- generic sparse-embedding-gradient building blocks (K5/K6 in SURVEY.md section 2b) ---- */
+/* range-check idx[0..n) against rows->n_rows and give every distinct row a slot in the entity's
+ * compact gradient scratch (ws: BRS_STEP_WS_BYTES of zeroed device scratch; ws.err_flag collects errors) */
+int brs_rows_assign(const brs_rowset *rows, const int64_t *idx, int64_t n, void *ws, void *stream);
+/* grad_scratch[slot(idx[k])] += scale * src[k, :]   (src is [n, dim] of entity->table[table]) */
+int brs_rows_scatter_grad(const brs_entity *entity, int32_t table, const int64_t *idx, int64_t n, const float *src,
+                          float scale, void *stream);
 /* touched rows only: p -= lr*g (exactly what torch.optim.SGD does, g = 0 elsewhere) */
 int brs_rows_sgd(const brs_entity *entities, int32_t n_entities, double lr, void *stream);
 /* touched rows only, Adam with explicit step number t (1-based) */

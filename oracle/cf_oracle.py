@@ -191,6 +191,30 @@ def mf_bce_loss_grads(p, users, items, ratings, reg_w=0.0):
     return loss, reg, g
 
 
+def mf_condition_scale(p, batch, loss="bpr"):
+    """Per parameter tensor, max over elements of sum_k |term_k| of its gradient sum
+    (the forward-error scale of an fp32 summation: |fl(sum) - sum| <= c*eps*sum|terms|).
+    Bias gradients add opposite-sign terms (c_pos < 0 < c_neg) and can cancel to ~0,
+    so parity of such entries is judged against this scale, not against |result|."""
+    pa = {k: np.abs(v) for k, v in p.items()}
+    g = _mf_zero_grads(p)
+    b = len(batch[0])
+    dt = p["user_emb.weight"].dtype.type
+    if loss == "bpr":
+        users, pos, neg = batch
+        sp_, _ = mf_forward(p, users, pos)
+        sn_, _ = mf_forward(p, users, neg)
+        dx = sigmoid(-(sp_ - sn_)) / dt(b)
+        _mf_accumulate(pa, g, users, pos, np.abs(dx * sp_ * (1 - sp_)), 0.0, b)
+        _mf_accumulate(pa, g, users, neg, np.abs(dx * sn_ * (1 - sn_)), 0.0, b)
+    else:
+        users, items, ratings = batch
+        s, _ = mf_forward(p, users, items)
+        _, ds = bce_loss_and_grad(s, ratings.astype(s.dtype))
+        _mf_accumulate(pa, g, users, items, np.abs(ds * s * (1 - s)), 0.0, b)
+    return {k: float(np.abs(v).max()) for k, v in g.items()}
+
+
 def mf_train_single_batch(p, st, batch, loss="bpr", optimizer="sgd", lr=0.05, reg_w=0.0):
     """One MFEngine.train_single_batch (beta_rec/models/mf.py:92-119): returns
     (loss, regularizer) and updates p/st in place, batch-synchronously."""
