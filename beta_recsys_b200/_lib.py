@@ -74,6 +74,8 @@ _PROTOTYPES = {
     "brs_device_info": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
                                   C.POINTER(C.c_int64)]),
     "brs_mf_bpr_fwd_bwd": (C.c_int, [C.POINTER(MfModel), _P, _P, _P, C.c_int64, C.c_float, _P]),
+    "brs_mf_bpr_prepare": (C.c_int, [C.POINTER(MfModel), _P, _P, _P, C.c_int64, _P]),
+    "brs_mf_bpr_fwd_bwd_prepared": (C.c_int, [C.POINTER(MfModel), _P, _P, _P, C.c_int64, C.c_float, _P]),
     "brs_mf_bce_fwd_bwd": (C.c_int, [C.POINTER(MfModel), _P, _P, _P, C.c_int64, C.c_float, _P]),
     "brs_mf_apply": (C.c_int, [C.POINTER(MfModel), C.POINTER(Opt), C.c_int64, _P, _P]),
     "brs_mf_train_batches": (C.c_int, [C.POINTER(MfModel), C.POINTER(Opt), C.c_int32, _P, _P, _P, C.c_int64,

@@ -398,8 +398,17 @@ int fill_args(const brs_mf_model* m, MfArgs& a, bool need_grad) {
 
 }  // namespace
 
+// phases: 1 = slot pre-pass, 2 = fused kernel, 3 = both
+int brs_mf_fwd_bwd_phases(const brs_mf_model* model, int loss_kind, const int64_t* users, const int64_t* items,
+                          const void* third, int64_t batch, float reg_weight, void* stream, int phases);
+
 int brs_mf_fwd_bwd_impl(const brs_mf_model* model, int loss_kind, const int64_t* users, const int64_t* items,
                         const void* third, int64_t batch, float reg_weight, void* stream) {
+    return brs_mf_fwd_bwd_phases(model, loss_kind, users, items, third, batch, reg_weight, stream, 3);
+}
+
+int brs_mf_fwd_bwd_phases(const brs_mf_model* model, int loss_kind, const int64_t* users, const int64_t* items,
+                          const void* third, int64_t batch, float reg_weight, void* stream, int phases) {
     if (!users || !items || !third || batch < 0) return BRS_ERR_INVALID_ARG;
     MfArgs a;
     int rc = fill_args(model, a, true);
@@ -412,13 +421,14 @@ int brs_mf_fwd_bwd_impl(const brs_mf_model* model, int loss_kind, const int64_t*
     a.reg_w = reg_weight;
     a.inv_b = 1.0f / (float)batch;
     cudaStream_t st = (cudaStream_t)stream;
-    {   // pre-pass: range-check the indices and give every touched row a slot in the compact scratch
+    if (phases & 1) {  // pre-pass: range-check the indices and give every touched row a slot in the compact scratch
         const brs_rowset rs[3] = {model->user.rows, model->item.rows, model->item.rows};
         const long long* idx[3] = {(const long long*)users, (const long long*)items, (const long long*)third};
         const long long n[3] = {batch, batch, batch};
         rc = brs_assign_slots(rs, idx, n, loss_kind == LOSS_BPR ? 3 : 2, a.ws, st);
         if (rc != BRS_OK) return rc;
     }
+    if (!(phases & 2)) return BRS_OK;
     if (loss_kind == LOSS_BPR) return launch_fwd_bwd<LOSS_BPR>(a, st);
     if (loss_kind == LOSS_BCE) return launch_fwd_bwd<LOSS_BCE>(a, st);
     return BRS_ERR_INVALID_ARG;
@@ -427,6 +437,16 @@ int brs_mf_fwd_bwd_impl(const brs_mf_model* model, int loss_kind, const int64_t*
 extern "C" int brs_mf_bpr_fwd_bwd(const brs_mf_model* model, const int64_t* users, const int64_t* pos_items,
                                   const int64_t* neg_items, int64_t batch, float reg_weight, void* stream) {
     return brs_mf_fwd_bwd_impl(model, LOSS_BPR, users, pos_items, neg_items, batch, reg_weight, stream);
+}
+
+// the two launches of brs_mf_bpr_fwd_bwd individually (profiling / per-kernel timing)
+extern "C" int brs_mf_bpr_prepare(const brs_mf_model* model, const int64_t* users, const int64_t* pos_items,
+                                  const int64_t* neg_items, int64_t batch, void* stream) {
+    return brs_mf_fwd_bwd_phases(model, LOSS_BPR, users, pos_items, neg_items, batch, 0.f, stream, 1);
+}
+extern "C" int brs_mf_bpr_fwd_bwd_prepared(const brs_mf_model* model, const int64_t* users, const int64_t* pos_items,
+                                           const int64_t* neg_items, int64_t batch, float reg_weight, void* stream) {
+    return brs_mf_fwd_bwd_phases(model, LOSS_BPR, users, pos_items, neg_items, batch, reg_weight, stream, 2);
 }
 
 extern "C" int brs_mf_bce_fwd_bwd(const brs_mf_model* model, const int64_t* users, const int64_t* items,

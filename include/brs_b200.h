@@ -140,6 +140,14 @@ int brs_device_info(int device, int *sm_count, int *cc_major, int *cc_minor, int
 int brs_mf_bpr_fwd_bwd(const brs_mf_model *model, const int64_t *users, const int64_t *pos_items,
                        const int64_t *neg_items, int64_t batch, float reg_weight, void *stream);
 
+/* brs_mf_bpr_fwd_bwd = brs_mf_bpr_prepare (slot pre-pass: range check + one slot of the compact gradient
+ * scratch per touched row) followed by brs_mf_bpr_fwd_bwd_prepared (the fused kernel); exposed separately
+ * so that each launch can be timed / profiled on its own */
+int brs_mf_bpr_prepare(const brs_mf_model *model, const int64_t *users, const int64_t *pos_items,
+                       const int64_t *neg_items, int64_t batch, void *stream);
+int brs_mf_bpr_fwd_bwd_prepared(const brs_mf_model *model, const int64_t *users, const int64_t *pos_items,
+                                const int64_t *neg_items, int64_t batch, float reg_weight, void *stream);
+
 /* Same for loss == "bce" (beta_rec/models/mf.py:108-111; torch_engine.py:108-121, nn.BCELoss). */
 int brs_mf_bce_fwd_bwd(const brs_mf_model *model, const int64_t *users, const int64_t *items,
                        const float *ratings, int64_t batch, float reg_weight, void *stream);
