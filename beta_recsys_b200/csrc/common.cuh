@@ -90,26 +90,11 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src
 }
 
 // ---------------------------------------------------------------------------
-// touched-row bookkeeping: the first toucher of a row claims the next slot of the
-// entity's compact gradient scratch (assign_slots_kernel, rows_apply.cu)
+// touched-row bookkeeping: slot_map values (assign_slots_kernel in rows_apply.cu: the
+// first toucher of a row claims the next slot of the entity's compact gradient scratch)
 // ---------------------------------------------------------------------------
 #define BRS_SLOT_NONE (-1)
 #define BRS_SLOT_PENDING (-2)
-
-__device__ __forceinline__ void claim_slot(const brs_rowset& rs, long long row, unsigned int* err_flag) {
-    int* m = rs.slot_map + row;
-    if (*((volatile int*)m) != BRS_SLOT_NONE) return;  // hot (Zipf) rows are claimed by the time most samples arrive
-    if (atomicCAS(m, BRS_SLOT_NONE, BRS_SLOT_PENDING) == BRS_SLOT_NONE) {
-        const int slot = atomicAdd(rs.count, 1);
-        if (slot < rs.capacity) {
-            rs.list[slot] = (int)row;
-            *((volatile int*)m) = slot;  // consumers run in later kernels of the same stream
-        } else {
-            *((volatile int*)m) = BRS_SLOT_NONE;
-            if (err_flag) atomicOr(err_flag, 2u);
-        }
-    }
-}
 
 // ---------------------------------------------------------------------------
 // scalar math exactly as ATen evaluates it in fp32

@@ -13,15 +13,15 @@
 // (rows_apply.cu) so that every sample reads PRE-step weights (batch-synchronous
 // semantics of autograd + torch.optim).
 //
-// Shape of the launch (from the round-1 ncu capture: the kernel is latency-bound,
-// not atomic- or bandwidth-bound): one 64-sample tile per 128-thread block so a
-// 65536-sample batch is 1024 co-resident blocks; each warp owns 16 samples and
-// keeps two passes (2 x SPW samples, 6 row loads per lane) in flight; nothing on
-// the per-sample path waits for an atomic's return value.
-//
-// Thread mapping: a row of D floats is covered by LPR = min(32, D/4) lanes x VPL
-// float4 each, so a warp handles SPW = 32/LPR samples per pass and every global
-// access of a lane group is one contiguous 16*LPR-byte segment.
+// Shape of the launch (from the round-1 ncu captures: v1 was latency-bound, v2
+// issue-bound at ~550 instructions per sample because all 32 lanes of a row group
+// repeated the scalar loss math): a row of D floats is covered by LPR lanes x VPL
+// float4 with VPL = 4 wherever D allows (D = 128 -> 8 lanes x 4), so every warp
+// instruction -- address math, shuffles, the sigmoid/log chain -- serves 32/LPR
+// samples at once, and each lane still issues 128-bit loads whose LPR-lane groups
+// cover whole 128-byte lines.  Persistent grid (resident blocks only), 32-sample
+// tiles double-buffered through TMA, warp-uniform loop control, nothing on the
+// per-sample path waits for an atomic's return value.
 #include "common.cuh"
 
 int brs_assign_slots(const brs_rowset* rs, const long long* const* idx, const long long* n, int n_arrays,
@@ -31,7 +31,7 @@ namespace {
 
 constexpr int kThreads = 128;
 constexpr int kWarps = kThreads / 32;
-constexpr int kTile = 64;  // samples per block (one staged index tile)
+constexpr int kTile = 32;  // samples per staged index tile (double-buffered)
 
 enum { LOSS_BPR = 0, LOSS_BCE = 1 };
 
@@ -101,9 +101,10 @@ __device__ __forceinline__ void sample_load(const MfArgs& a, const IdxTile& T, i
         x.valid = false;  // flagged by the pre-pass (the reference raises IndexError)
         x.u = x.i = x.j = 0;
     }
-    const float* ur = a.user_emb + x.u * D;
-    const float* ir = a.item_emb + x.i * D;
-    const float* jr = a.item_emb + x.j * D;
+    // rows < 2^31 (slot maps are int32), so one 32x32->64 IMAD.WIDE per row address
+    const float* ur = a.user_emb + (unsigned long long)((unsigned)x.u) * (unsigned)D;
+    const float* ir = a.item_emb + (unsigned long long)((unsigned)x.i) * (unsigned)D;
+    const float* jr = a.item_emb + (unsigned long long)((unsigned)x.j) * (unsigned)D;
 #pragma unroll
     for (int v = 0; v < VPL; ++v) {
         const int col = (v * LPR + gl) * 4;
@@ -167,9 +168,9 @@ __device__ __forceinline__ void sample_finish(const MfArgs& a, const Sample<VPL,
         gb_acc += cu_i + cu_j;
     }
     const float rw = 2.0f * a.reg_w * a.inv_b;  // d(reg_w*regularizer)/d row = rw * row per forward call
-    float* gu = a.g_user_emb + (long long)x.su * D;
-    float* gi = a.g_item_emb + (long long)x.si * D;
-    float* gj = a.g_item_emb + (long long)x.sj * D;
+    float* gu = a.g_user_emb + (unsigned long long)((unsigned)x.su) * (unsigned)D;
+    float* gi = a.g_item_emb + (unsigned long long)((unsigned)x.si) * (unsigned)D;
+    float* gj = a.g_item_emb + (unsigned long long)((unsigned)x.sj) * (unsigned)D;
 #pragma unroll
     for (int v = 0; v < VPL; ++v) {
         const int col = (v * LPR + gl) * 4;
@@ -194,60 +195,93 @@ __device__ __forceinline__ void sample_finish(const MfArgs& a, const Sample<VPL,
     if (LOSS == LOSS_BPR && gl == 2 % LPR) red_add1(a.g_item_bias + x.sj, cu_j + rw * x.bj);
 }
 
-template <int LPR, int VPL, bool FULL, int LOSS>
-__global__ void __launch_bounds__(kThreads, (VPL == 1) ? 8 : 4) mf_fwd_bwd_kernel(const MfArgs a) {
-    constexpr int SPW = 32 / LPR;
-    __shared__ IdxTile s_tile;
-    __shared__ __align__(8) uint64_t s_bar;
-    __shared__ float s_red[3][kWarps];
-
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    const int gl = lane % LPR;   // lane within the row group
-    const int grp = lane / LPR;  // which of the warp's SPW samples
-    const int D = a.dim;
-    const long long base = (long long)blockIdx.x * kTile;
-    const int tile_n = (int)min((long long)kTile, a.batch - base);
-
-    // ---- stage this block's slice of the index lists: TMA when the slice is a full,
-    //      16-byte aligned tile; plain loads for the ragged tail / odd views ----
+// Stage tile `t` of the batch's index lists into `dst`.  TMA path when the slice is a
+// full, 16-byte aligned tile; otherwise (ragged tail / odd views) the block copies it
+// with plain loads.  Returns whether the TMA path was taken (block-uniform).
+template <int LOSS>
+__device__ __forceinline__ bool stage_tile(const MfArgs& a, long long t, IdxTile* dst, uint64_t* bar) {
+    const long long base = t * kTile;
+    const long long n = min((long long)kTile, a.batch - base);
     const long long* pa = a.users + base;
     const long long* pb = a.items + base;
     const char* pc = (const char*)a.third + base * (LOSS == LOSS_BPR ? 8 : 4);
     constexpr unsigned bytes_c = (LOSS == LOSS_BPR ? 8u : 4u) * kTile;
-    const bool use_tma = (tile_n == kTile) && ((((uintptr_t)pa | (uintptr_t)pb | (uintptr_t)pc) & 15) == 0);
-    if (use_tma) {
+    const bool used_tma = (n == kTile) && ((((uintptr_t)pa | (uintptr_t)pb | (uintptr_t)pc) & 15) == 0);
+    if (used_tma) {
         if (threadIdx.x == 0) {
-            mbar_init(&s_bar, 1);
-            mbar_fence_init();
-            mbar_expect_tx(&s_bar, 2u * 8u * kTile + bytes_c);
-            tma_load_1d(s_tile.a, pa, 8u * kTile, &s_bar);
-            tma_load_1d(s_tile.b, pb, 8u * kTile, &s_bar);
-            tma_load_1d(s_tile.c, pc, bytes_c, &s_bar);
+            mbar_expect_tx(bar, 2u * 8u * kTile + bytes_c);
+            tma_load_1d(dst->a, pa, 8u * kTile, bar);
+            tma_load_1d(dst->b, pb, 8u * kTile, bar);
+            tma_load_1d(dst->c, pc, bytes_c, bar);
         }
-        __syncthreads();  // barrier object initialised before anyone polls it
-        mbar_wait(&s_bar, 0u);
     } else {
-        for (int k = threadIdx.x; k < tile_n; k += kThreads) {
-            s_tile.a[k] = pa[k];
-            s_tile.b[k] = pb[k];
+        for (int k = threadIdx.x; k < n; k += kThreads) {
+            dst->a[k] = pa[k];
+            dst->b[k] = pb[k];
             if (LOSS == LOSS_BPR)
-                s_tile.c[k] = ((const long long*)pc)[k];
+                dst->c[k] = ((const long long*)pc)[k];
             else
-                ((float*)s_tile.c)[k] = ((const float*)pc)[k];
+                ((float*)dst->c)[k] = ((const float*)pc)[k];
         }
-        __syncthreads();
     }
+    return used_tma;
+}
+
+template <int LPR, int VPL, bool FULL, int LOSS>
+__global__ void __launch_bounds__(kThreads, (VPL <= 2) ? 8 : 5) mf_fwd_bwd_kernel(const MfArgs a) {
+    constexpr int SPW = 32 / LPR;
+    __shared__ IdxTile s_tile[2];
+    __shared__ __align__(8) uint64_t s_bar[2];
+    __shared__ float s_red[3][kWarps];
+
+    const int lane = threadIdx.x & 31;
+    // broadcast from lane 0 so the compiler knows the value (and every loop bound built
+    // from it) is warp-uniform: shuffles below need no divergence guards
+    const int warp = __shfl_sync(BRS_FULL_MASK, threadIdx.x >> 5, 0);
+    const int gl = lane % LPR;   // lane within the row group
+    const int grp = lane / LPR;  // which of the warp's SPW samples
+    const int D = a.dim;
+    const long long n_tiles = (a.batch + kTile - 1) / kTile;
+
+    if (threadIdx.x == 0) {
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
 
     const float bg = __ldg(a.global_bias);
     float loss_acc = 0.f, reg_acc = 0.f, gb_acc = 0.f;
-    // two passes (2*SPW samples) in flight per warp
-    for (int b0 = warp * SPW; b0 < tile_n; b0 += 2 * kWarps * SPW) {
-        Sample<VPL, LOSS> x0, x1;
-        sample_load<LPR, VPL, FULL, LOSS>(a, s_tile, b0 + grp, tile_n, gl, D, x0);
-        sample_load<LPR, VPL, FULL, LOSS>(a, s_tile, b0 + kWarps * SPW + grp, tile_n, gl, D, x1);
-        sample_finish<LPR, VPL, FULL, LOSS>(a, x0, gl, D, bg, loss_acc, reg_acc, gb_acc);
-        sample_finish<LPR, VPL, FULL, LOSS>(a, x1, gl, D, bg, loss_acc, reg_acc, gb_acc);
+    unsigned phase_bits = 0u;  // bit b = parity to wait for on s_bar[b]
+    unsigned tma_bits = 0u;    // bit b = s_tile[b] is being filled by TMA
+
+    long long t = blockIdx.x;
+    int buf = 0;
+    if (t < n_tiles && stage_tile<LOSS>(a, t, &s_tile[0], &s_bar[0])) tma_bits |= 1u;
+
+    for (; t < n_tiles; t += gridDim.x, buf ^= 1) {
+        const long long tn = t + gridDim.x;
+        // prefetch the next tile into the other buffer (its previous readers passed the
+        // __syncthreads at the end of the previous iteration)
+        if (tn < n_tiles) {
+            const bool nt = stage_tile<LOSS>(a, tn, &s_tile[buf ^ 1], &s_bar[buf ^ 1]);
+            tma_bits = (tma_bits & ~(1u << (buf ^ 1))) | ((nt ? 1u : 0u) << (buf ^ 1));
+        }
+        if ((tma_bits >> buf) & 1u) {
+            mbar_wait(&s_bar[buf], (phase_bits >> buf) & 1u);
+            phase_bits ^= 1u << buf;
+        } else {
+            __syncthreads();  // plain-copy path: make the block's stores visible
+        }
+        const IdxTile& T = s_tile[buf];
+        const int tile_n = (int)min((long long)kTile, a.batch - t * kTile);
+
+        for (int b0 = warp * SPW; b0 < tile_n; b0 += kWarps * SPW) {
+            Sample<VPL, LOSS> x;
+            sample_load<LPR, VPL, FULL, LOSS>(a, T, b0 + grp, tile_n, gl, D, x);
+            sample_finish<LPR, VPL, FULL, LOSS>(a, x, gl, D, bg, loss_acc, reg_acc, gb_acc);
+        }
+        __syncthreads();  // everyone is done with s_tile[buf] before it is refilled
     }
 
     // block reduction of the scalar outputs -> 3 atomics per block
@@ -324,21 +358,20 @@ template <int LOSS>
 int launch_fwd_bwd(const MfArgs& a, cudaStream_t st) {
     const int D = a.dim;
     const long long n_tiles = (a.batch + kTile - 1) / kTile;
-    if (n_tiles > 0x7fffffffLL) return BRS_ERR_INVALID_ARG;
 #define BRS_LAUNCH(LPR, VPL, FULL)                                                      \
     do {                                                                                \
         auto k = mf_fwd_bwd_kernel<LPR, VPL, FULL, LOSS>;                               \
-        k<<<(int)n_tiles, kThreads, 0, st>>>(a); /* one tile per block */               \
+        k<<<grid_for((const void*)k, n_tiles), kThreads, 0, st>>>(a);                   \
     } while (0)
     if (D % 4 != 0 || D <= 0 || D > 512) return BRS_ERR_UNSUPPORTED;
-    switch (D) {
+    switch (D) {  // VPL = 4 float4 per lane wherever D allows: a warp instruction serves 32/LPR samples
         case 4: BRS_LAUNCH(1, 1, true); break;
-        case 8: BRS_LAUNCH(2, 1, true); break;
-        case 16: BRS_LAUNCH(4, 1, true); break;
-        case 32: BRS_LAUNCH(8, 1, true); break;
-        case 64: BRS_LAUNCH(16, 1, true); break;
-        case 128: BRS_LAUNCH(32, 1, true); break;
-        case 256: BRS_LAUNCH(32, 2, true); break;
+        case 8: BRS_LAUNCH(1, 2, true); break;
+        case 16: BRS_LAUNCH(1, 4, true); break;
+        case 32: BRS_LAUNCH(2, 4, true); break;
+        case 64: BRS_LAUNCH(4, 4, true); break;
+        case 128: BRS_LAUNCH(8, 4, true); break;
+        case 256: BRS_LAUNCH(16, 4, true); break;
         case 384: BRS_LAUNCH(32, 3, true); break;
         case 512: BRS_LAUNCH(32, 4, true); break;
         default:  // any other multiple of 4: next power-of-two lane group, tail lanes idle

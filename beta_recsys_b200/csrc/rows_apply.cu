@@ -32,22 +32,64 @@ struct AssignArgs {
     brs_rowset rs[kMaxAssign];
     const long long* idx[kMaxAssign];
     long long n[kMaxAssign];
-    long long offset[kMaxAssign + 1];
     int n_arrays;
     unsigned int* err_flag;
 };
 
+// grid = (blocks, n_arrays): every block works on ONE index array, so all of its claims go to
+// one rowset and are aggregated into a single atomicAdd on that rowset's counter (the v1
+// per-thread atomicAdd on one address was 55% of this kernel's stall samples).
 __global__ void __launch_bounds__(kThreads) assign_slots_kernel(const AssignArgs a) {
-    const long long total = a.offset[a.n_arrays];
-    for (long long t = (long long)blockIdx.x * kThreads + threadIdx.x; t < total; t += (long long)gridDim.x * kThreads) {
-        int k = 0;
-        while (k + 1 < a.n_arrays && t >= a.offset[k + 1]) ++k;
-        const long long row = a.idx[k][t - a.offset[k]];
-        if ((unsigned long long)row >= (unsigned long long)a.rs[k].n_rows) {
-            atomicOr(a.err_flag, 1u);  // the reference raises IndexError (nn.Embedding)
-            continue;
+    __shared__ int s_warp_cnt[kWarps];
+    __shared__ int s_base;
+    const int k = blockIdx.y;
+    const brs_rowset rs = a.rs[k];
+    const long long* __restrict__ idx = a.idx[k];
+    const long long n = a.n[k];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long stride = (long long)gridDim.x * kThreads;
+    const long long n_iter = (n + stride - 1) / stride;
+    for (long long it = 0; it < n_iter; ++it) {
+        const long long t = it * stride + (long long)blockIdx.x * kThreads + threadIdx.x;
+        long long row = -1;
+        bool won = false;
+        if (t < n) {
+            row = idx[t];
+            if ((unsigned long long)row >= (unsigned long long)rs.n_rows) {
+                atomicOr(a.err_flag, 1u);  // the reference raises IndexError (nn.Embedding)
+                row = -1;
+            } else {
+                int* m = rs.slot_map + row;
+                // cheap read first: hot (Zipf) rows are claimed by the time most samples arrive
+                if (*((volatile int*)m) == BRS_SLOT_NONE) won = atomicCAS(m, BRS_SLOT_NONE, BRS_SLOT_PENDING) == BRS_SLOT_NONE;
+            }
         }
-        claim_slot(a.rs[k], row, a.err_flag);
+        const unsigned ballot = __ballot_sync(BRS_FULL_MASK, won);
+        const int lane_off = __popc(ballot & ((1u << lane) - 1u));
+        if (lane == 0) s_warp_cnt[warp] = __popc(ballot);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int tot = 0;
+#pragma unroll
+            for (int w = 0; w < kWarps; ++w) {
+                const int c = s_warp_cnt[w];
+                s_warp_cnt[w] = tot;
+                tot += c;
+            }
+            s_base = tot ? atomicAdd(rs.count, tot) : 0;
+        }
+        __syncthreads();
+        if (won) {
+            const int slot = s_base + s_warp_cnt[warp] + lane_off;
+            if (slot < rs.capacity) {
+                rs.list[slot] = (int)row;
+                rs.slot_map[row] = slot;  // consumers run in later kernels of the same stream
+            } else {
+                rs.slot_map[row] = BRS_SLOT_NONE;
+                atomicOr(a.err_flag, 2u);
+            }
+        }
+        __syncthreads();  // s_warp_cnt / s_base are reused by the next iteration
     }
 }
 
@@ -158,31 +200,38 @@ __device__ __forceinline__ void update_row(const brs_table& tb, long long row, l
     }
 }
 
-// fast path: ROWS touched rows of a dim <= 128 (dim % 4 == 0) table in flight per warp
+// fast path: ROWS touched rows of a (dim % 4 == 0, dim <= 128) table in flight per warp.
+// SGD needs no weight load at all: w += -lr*g leaves as a fire-and-forget 128-bit RED.
 template <int KIND, int ROWS>
-__device__ __forceinline__ void update_rows_small(const brs_table& tb, const long long* row, const long long* slot,
-                                                  int n, int lane, const OptScalars& s) {
+__device__ __forceinline__ void update_rows_small(const brs_table& tb, const int (&row)[ROWS], int s0, int n, int lane,
+                                                  const OptScalars& s) {
     const int d = tb.dim, c = lane * 4;
     if (c >= d) return;
     float4 gv[ROWS], wv[ROWS], mv[ROWS], vv[ROWS];
 #pragma unroll
     for (int r = 0; r < ROWS; ++r) {
-        mv[r] = vv[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+        wv[r] = mv[r] = vv[r] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (r < n) {
-            gv[r] = *(const float4*)(tb.grad + slot[r] * d + c);
-            wv[r] = *(const float4*)(tb.weight + row[r] * d + c);
-            if (KIND == BRS_ADAM) mv[r] = *(const float4*)(tb.m + row[r] * d + c);
-            if (KIND != BRS_SGD) vv[r] = *(const float4*)(tb.v + row[r] * d + c);
+            const size_t ro = (size_t)(unsigned)row[r] * (unsigned)d + c;
+            gv[r] = *(const float4*)(tb.grad + (size_t)(unsigned)(s0 + r) * (unsigned)d + c);
+            if (KIND != BRS_SGD) wv[r] = *(const float4*)(tb.weight + ro);
+            if (KIND == BRS_ADAM) mv[r] = *(const float4*)(tb.m + ro);
+            if (KIND != BRS_SGD) vv[r] = *(const float4*)(tb.v + ro);
         }
     }
 #pragma unroll
     for (int r = 0; r < ROWS; ++r) {
         if (r < n) {
-            opt_elem4<KIND>(wv[r], gv[r], mv[r], vv[r], s);
-            *(float4*)(tb.weight + row[r] * d + c) = wv[r];
-            if (KIND == BRS_ADAM) *(float4*)(tb.m + row[r] * d + c) = mv[r];
-            if (KIND != BRS_SGD) *(float4*)(tb.v + row[r] * d + c) = vv[r];
-            *(float4*)(tb.grad + slot[r] * d + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+            const size_t ro = (size_t)(unsigned)row[r] * (unsigned)d + c;
+            if (KIND == BRS_SGD) {
+                red_add4(tb.weight + ro, make_float4(-s.lr * gv[r].x, -s.lr * gv[r].y, -s.lr * gv[r].z, -s.lr * gv[r].w));
+            } else {
+                opt_elem4<KIND>(wv[r], gv[r], mv[r], vv[r], s);
+                *(float4*)(tb.weight + ro) = wv[r];
+                if (KIND == BRS_ADAM) *(float4*)(tb.m + ro) = mv[r];
+                *(float4*)(tb.v + ro) = vv[r];
+            }
+            *(float4*)(tb.grad + (size_t)(unsigned)(s0 + r) * (unsigned)d + c) = make_float4(0.f, 0.f, 0.f, 0.f);
         }
     }
 }
@@ -266,49 +315,48 @@ template <int KIND>
 __global__ void __launch_bounds__(kThreads) rows_apply_kernel(const ApplyArgs a) {
     constexpr int ROWS = 4;
     __shared__ OptScalars s_opt;
-    __shared__ int s_cnt[kMaxEntities + 1];
+    __shared__ int s_cnt[kMaxEntities + 1];  // prefix of work items (groups of ROWS slots)
+    __shared__ int s_rows[kMaxEntities];     // touched rows per entity
     if (threadIdx.x == 0) {
         const long long t = a.ws ? a.ws->step + 1 : a.t_explicit;
         s_opt = make_scalars(a.opt, t);
         int acc = 0;
         for (int e = 0; e < a.n_ent; ++e) {
             s_cnt[e] = acc;
-            acc += (clamped_count(a.ent[e].rows) + ROWS - 1) / ROWS;  // work items = groups of ROWS slots
+            s_rows[e] = clamped_count(a.ent[e].rows);
+            acc += (s_rows[e] + ROWS - 1) / ROWS;
         }
         s_cnt[a.n_ent] = acc;
     }
     __syncthreads();
     const OptScalars s = s_opt;
     const int lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(BRS_FULL_MASK, threadIdx.x >> 5, 0);
     const int total = s_cnt[a.n_ent];
-    for (int r = blockIdx.x * kWarps + (threadIdx.x >> 5); r < total; r += gridDim.x * kWarps) {
+    for (int r = blockIdx.x * kWarps + warp; r < total; r += gridDim.x * kWarps) {
         int e = 0;
         while (e + 1 < a.n_ent && r >= s_cnt[e + 1]) ++e;
         const brs_entity& en = a.ent[e];
-        const int cnt = clamped_count(en.rows);
         const int s0 = (r - s_cnt[e]) * ROWS;
-        const int n = min(ROWS, cnt - s0);
-        long long row[ROWS], slot[ROWS];
+        const int n = min(ROWS, s_rows[e] - s0);
+        // lanes 0..ROWS-1 fetch the row ids, everyone gets them by shuffle (registers, no local memory)
+        const int my_row = (lane < n) ? en.rows.list[s0 + lane] : 0;
+        int row[ROWS];
 #pragma unroll
-        for (int k = 0; k < ROWS; ++k) {
-            slot[k] = s0 + k;
-            row[k] = (k < n) ? en.rows.list[s0 + k] : 0;
-        }
+        for (int k = 0; k < ROWS; ++k) row[k] = __shfl_sync(BRS_FULL_MASK, my_row, k);
         for (int k = 0; k < en.n_tables; ++k) {
             const brs_table& tb = en.table[k];
             if ((tb.dim & 3) == 0 && tb.dim <= 128) {
-                update_rows_small<KIND, ROWS>(tb, row, slot, n, lane, s);
-            } else if (tb.dim == 1) {  // bias tables: one lane per row
+                update_rows_small<KIND, ROWS>(tb, row, s0, n, lane, s);
+            } else if (tb.dim == 1) {  // bias tables: lane q handles row q
+                if (lane < n) update_row<KIND>(tb, my_row, s0 + lane, 0, s);
+            } else {
 #pragma unroll
                 for (int q = 0; q < ROWS; ++q)
-                    if (lane == q && q < n) update_row<KIND>(tb, row[q], slot[q], 0, s);
-            } else {
-                for (int q = 0; q < n; ++q) update_row<KIND>(tb, row[q], slot[q], lane, s);
+                    if (q < n) update_row<KIND>(tb, row[q], s0 + q, lane, s);
             }
         }
-#pragma unroll
-        for (int q = 0; q < ROWS; ++q)
-            if (lane == q && q < n) en.rows.slot_map[row[q]] = BRS_SLOT_NONE;  // release the slot
+        if (lane < n) en.rows.slot_map[my_row] = BRS_SLOT_NONE;  // release the slot
     }
     dense_params_update<KIND>(a, s);
     if (a.ws) {
@@ -520,23 +568,21 @@ int brs_assign_slots(const brs_rowset* rs, const long long* const* idx, const lo
     if (n_arrays < 1 || n_arrays > kMaxAssign || !ws) return BRS_ERR_INVALID_ARG;
     AssignArgs a;
     memset(&a, 0, sizeof(a));
-    long long off = 0;
+    long long nmax = 0;
     for (int k = 0; k < n_arrays; ++k) {
         if (!rs[k].slot_map || !rs[k].list || !rs[k].count || !idx[k] || n[k] < 0) return BRS_ERR_INVALID_ARG;
         a.rs[k] = rs[k];
         a.idx[k] = idx[k];
         a.n[k] = n[k];
-        a.offset[k] = off;
-        off += n[k];
+        if (n[k] > nmax) nmax = n[k];
     }
-    a.offset[n_arrays] = off;
     a.n_arrays = n_arrays;
     a.err_flag = &ws->err_flag;
-    if (off == 0) return BRS_OK;
-    long long blocks = (off + kThreads - 1) / kThreads;
-    const long long cap = (long long)brs_sm_count() * 8;
+    if (nmax == 0) return BRS_OK;
+    long long blocks = (nmax + kThreads - 1) / kThreads;
+    const long long cap = (long long)brs_sm_count() * 4;
     if (blocks > cap) blocks = cap;
-    assign_slots_kernel<<<(int)blocks, kThreads, 0, st>>>(a);
+    assign_slots_kernel<<<dim3((unsigned)blocks, (unsigned)n_arrays), kThreads, 0, st>>>(a);
     BRS_CUDA_CHECK(cudaGetLastError());
     return BRS_OK;
 }
