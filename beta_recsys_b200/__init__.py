@@ -5,3 +5,4 @@ __version__ = "0.1.0"
 
 from . import _lib  # noqa: F401
 from ._lib import BrsError  # noqa: F401
+from .install import install, uninstall  # noqa: F401,E402

@@ -23,14 +23,29 @@ static_assert(sizeof(brs_step_ws) <= BRS_STEP_WS_BYTES, "ws layout");
 // ---------------------------------------------------------------------------
 // memory ops
 // ---------------------------------------------------------------------------
-// 128-bit gather load.  Rows are re-read by other samples of the batch (Zipf
-// duplicates) so they stay on the default (L2-allocating) path; L1 is bypassed.
+// 128-bit gather load of an embedding row on the read-only (L1-allocating) path: tables are
+// never written by the kernels that gather them, and under Zipf indices the hot rows are
+// re-read dozens of times per SM -- L1 hits keep those reads off the two L2 slices a 512-byte
+// row hashes to (round-1 profile: the hottest row is ~10% of a batch).
 __device__ __forceinline__ float4 ld_row4(const float* p) {
     float4 r;
-    asm volatile("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+    asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];"
                  : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
                  : "l"(p));
     return r;
+}
+
+// Gradient-scratch layout.  For dim % 8 == 0 the compact scratch of a table is stored
+// "sector-blocked": [dim/8][capacity][8 floats], i.e. element (slot, col) lives at
+//     ((col >> 3) * capacity + slot) * 8 + (col & 7).
+// The 32-byte sectors of one gradient row are then capacity*32 bytes apart and hash to
+// different L2 slices.  A B200 L2 slice retires ~1 RED sector per clock, and a row-major
+// 512-byte row maps to only TWO slices, so under Zipf indices the hottest row serialised
+// ~36 us of REDs on one slice (round-1 ncu: lts__d_atomic_input_cycles_active max 62%).
+// Other dims keep the row-major [capacity][dim] layout.
+__device__ __forceinline__ size_t gs_off(int dim, int capacity, unsigned slot, int col) {
+    return (dim & 7) ? (size_t)slot * (unsigned)dim + col
+                     : ((size_t)(col >> 3) * (unsigned)capacity + slot) * 8 + (col & 7);
 }
 
 // 128-bit fire-and-forget scatter-add (sm_90+): one L2 reduction per 16 bytes.

@@ -35,6 +35,30 @@ constexpr int kTile = 32;  // samples per staged index tile (double-buffered)
 
 enum { LOSS_BPR = 0, LOSS_BCE = 1 };
 
+struct MfPeerTables {  // one rank's shard, as seen from this process (device-resident array of these)
+    const float* user_emb;
+    const float* item_emb;
+    const float* user_bias;
+    const float* item_bias;
+    float* g_user_emb;
+    float* g_item_emb;
+    float* g_user_bias;
+    float* g_item_bias;
+    const int* user_slot;
+    const int* item_slot;
+};
+static_assert(sizeof(MfPeerTables) == sizeof(brs_mf_peer_tables), "peer table layout is part of the ABI");
+
+template <class T>
+__device__ __forceinline__ T* ldg_ptr(T* const* p) {
+    return (T*)__ldg((const unsigned long long*)p);
+}
+__device__ __forceinline__ int ld_volatile_s32(const int* p) {
+    int v;
+    asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+
 struct MfArgs {
     const float* __restrict__ user_emb;
     const float* __restrict__ item_emb;
@@ -47,6 +71,12 @@ struct MfArgs {
     float* g_item_bias;
     const int* __restrict__ user_slot;  // slot_map of the user rowset (filled by the pre-pass)
     const int* __restrict__ item_slot;
+    // row-sharded multi-GPU mode (SHARD = true): row r lives on rank r & shard_mask at local row
+    // r >> shard_shift; peers[rank] holds that rank's tables as pointers mapped into THIS process
+    // (NVLink peer memory), so gathers are peer loads and gradient scatters are peer REDs
+    const MfPeerTables* __restrict__ peers;
+    int shard_shift, shard_mask;
+    int user_cap, item_cap;  // capacity of the gradient scratch (sector-blocked layout, common.cuh gs_off)
     brs_step_ws* ws;
     const long long* users;
     const long long* items;  // pos items (bpr) / items (bce)
@@ -80,9 +110,10 @@ struct Sample {
     float4 ue[VPL], ie[VPL], je[VPL];
     float bu, bi, bj;
     int su, si, sj;  // gradient-scratch slots
+    int ou, oi, oj;  // owning ranks (SHARD only)
 };
 
-template <int LPR, int VPL, bool FULL, int LOSS>
+template <int LPR, int VPL, bool FULL, int LOSS, bool SHARD>
 __device__ __forceinline__ void sample_load(const MfArgs& a, const IdxTile& T, int s, int tile_n, int gl, int D,
                                             Sample<VPL, LOSS>& x) {
     x.valid = s < tile_n;
@@ -101,10 +132,34 @@ __device__ __forceinline__ void sample_load(const MfArgs& a, const IdxTile& T, i
         x.valid = false;  // flagged by the pre-pass (the reference raises IndexError)
         x.u = x.i = x.j = 0;
     }
+    // local row ids and the tables they live in (this rank's own, or a peer's under SHARD)
+    unsigned lu = (unsigned)x.u, li = (unsigned)x.i, lj = (unsigned)x.j;
+    const float *t_ue = a.user_emb, *t_ie = a.item_emb, *t_je = a.item_emb;
+    const float *t_ub = a.user_bias, *t_ib = a.item_bias, *t_jb = a.item_bias;
+    const int *t_us = a.user_slot, *t_is = a.item_slot, *t_js = a.item_slot;
+    x.ou = x.oi = x.oj = 0;
+    if (SHARD) {
+        x.ou = lu & a.shard_mask;
+        x.oi = li & a.shard_mask;
+        x.oj = lj & a.shard_mask;
+        lu >>= a.shard_shift;
+        li >>= a.shard_shift;
+        lj >>= a.shard_shift;
+        const MfPeerTables *pu = a.peers + x.ou, *pi = a.peers + x.oi, *pj = a.peers + x.oj;
+        t_ue = ldg_ptr(&pu->user_emb);
+        t_ie = ldg_ptr(&pi->item_emb);
+        t_je = ldg_ptr(&pj->item_emb);
+        t_ub = ldg_ptr(&pu->user_bias);
+        t_ib = ldg_ptr(&pi->item_bias);
+        t_jb = ldg_ptr(&pj->item_bias);
+        t_us = ldg_ptr(&pu->user_slot);
+        t_is = ldg_ptr(&pi->item_slot);
+        t_js = ldg_ptr(&pj->item_slot);
+    }
     // rows < 2^31 (slot maps are int32), so one 32x32->64 IMAD.WIDE per row address
-    const float* ur = a.user_emb + (unsigned long long)((unsigned)x.u) * (unsigned)D;
-    const float* ir = a.item_emb + (unsigned long long)((unsigned)x.i) * (unsigned)D;
-    const float* jr = a.item_emb + (unsigned long long)((unsigned)x.j) * (unsigned)D;
+    const float* ur = t_ue + (unsigned long long)lu * (unsigned)D;
+    const float* ir = t_ie + (unsigned long long)li * (unsigned)D;
+    const float* jr = t_je + (unsigned long long)lj * (unsigned)D;
 #pragma unroll
     for (int v = 0; v < VPL; ++v) {
         const int col = (v * LPR + gl) * 4;
@@ -113,16 +168,24 @@ __device__ __forceinline__ void sample_load(const MfArgs& a, const IdxTile& T, i
         x.ie[v] = on ? ld_row4(ir + col) : f4_zero();
         if (LOSS == LOSS_BPR) x.je[v] = on ? ld_row4(jr + col) : f4_zero();
     }
-    x.bu = __ldg(a.user_bias + x.u);
-    x.bi = __ldg(a.item_bias + x.i);
-    x.bj = (LOSS == LOSS_BPR) ? __ldg(a.item_bias + x.j) : 0.f;
-    x.su = __ldg(a.user_slot + x.u);
-    x.si = __ldg(a.item_slot + x.i);
-    x.sj = (LOSS == LOSS_BPR) ? __ldg(a.item_slot + x.j) : 0;
+    x.bu = __ldg(t_ub + lu);
+    x.bi = __ldg(t_ib + li);
+    x.bj = (LOSS == LOSS_BPR) ? __ldg(t_jb + lj) : 0.f;
+    if (!SHARD) {
+        x.su = __ldg(t_us + lu);
+        x.si = __ldg(t_is + li);
+        x.sj = (LOSS == LOSS_BPR) ? __ldg(t_js + lj) : 0;
+    } else {
+        // another rank may still be publishing the slot it claimed for this row: poll past PENDING
+        do { x.su = ld_volatile_s32(t_us + lu); } while (x.su == BRS_SLOT_PENDING && x.valid);
+        do { x.si = ld_volatile_s32(t_is + li); } while (x.si == BRS_SLOT_PENDING && x.valid);
+        x.sj = 0;
+        if (LOSS == LOSS_BPR) do { x.sj = ld_volatile_s32(t_js + lj); } while (x.sj == BRS_SLOT_PENDING && x.valid);
+    }
     if (x.su < 0 || x.si < 0 || x.sj < 0) x.valid = false;  // capacity overflow, flagged by the pre-pass
 }
 
-template <int LPR, int VPL, bool FULL, int LOSS>
+template <int LPR, int VPL, bool FULL, int LOSS, bool SHARD>
 __device__ __forceinline__ void sample_finish(const MfArgs& a, const Sample<VPL, LOSS>& x, int gl, int D, float bg,
                                               float& loss_acc, float& reg_acc, float& gb_acc) {
     float dp = 0.f, dn = 0.f, uu = 0.f, ii = 0.f, jj = 0.f;
@@ -168,9 +231,20 @@ __device__ __forceinline__ void sample_finish(const MfArgs& a, const Sample<VPL,
         gb_acc += cu_i + cu_j;
     }
     const float rw = 2.0f * a.reg_w * a.inv_b;  // d(reg_w*regularizer)/d row = rw * row per forward call
-    float* gu = a.g_user_emb + (unsigned long long)((unsigned)x.su) * (unsigned)D;
-    float* gi = a.g_item_emb + (unsigned long long)((unsigned)x.si) * (unsigned)D;
-    float* gj = a.g_item_emb + (unsigned long long)((unsigned)x.sj) * (unsigned)D;
+    float *t_gu = a.g_user_emb, *t_gi = a.g_item_emb, *t_gj = a.g_item_emb;
+    float *t_gub = a.g_user_bias, *t_gib = a.g_item_bias, *t_gjb = a.g_item_bias;
+    if (SHARD) {  // the owners' gradient scratch: the REDs below travel over NVLink
+        const MfPeerTables *pu = a.peers + x.ou, *pi = a.peers + x.oi, *pj = a.peers + x.oj;
+        t_gu = ldg_ptr(&pu->g_user_emb);
+        t_gi = ldg_ptr(&pi->g_item_emb);
+        t_gj = ldg_ptr(&pj->g_item_emb);
+        t_gub = ldg_ptr(&pu->g_user_bias);
+        t_gib = ldg_ptr(&pi->g_item_bias);
+        t_gjb = ldg_ptr(&pj->g_item_bias);
+    }
+    float* gu = t_gu;
+    float* gi = t_gi;
+    float* gj = t_gj;
 #pragma unroll
     for (int v = 0; v < VPL; ++v) {
         const int col = (v * LPR + gl) * 4;
@@ -178,21 +252,21 @@ __device__ __forceinline__ void sample_finish(const MfArgs& a, const Sample<VPL,
             float4 du = f4_scale(cu_i, x.ie[v]);
             if (LOSS == LOSS_BPR) du = f4_fma(cu_j, x.je[v], du);
             if (a.reg_w != 0.f) du = f4_fma(fwd_calls * rw, x.ue[v], du);
-            red_add4(gu + col, du);
+            red_add4(gu + gs_off(D, a.user_cap, (unsigned)x.su, col), du);
             float4 di = f4_scale(cu_i, x.ue[v]);
             if (a.reg_w != 0.f) di = f4_fma(rw, x.ie[v], di);
-            red_add4(gi + col, di);
+            red_add4(gi + gs_off(D, a.item_cap, (unsigned)x.si, col), di);
             if (LOSS == LOSS_BPR) {
                 float4 dj = f4_scale(cu_j, x.ue[v]);
                 if (a.reg_w != 0.f) dj = f4_fma(rw, x.je[v], dj);
-                red_add4(gj + col, dj);
+                red_add4(gj + gs_off(D, a.item_cap, (unsigned)x.sj, col), dj);
             }
         }
     }
     // bias gradients, spread over the first lanes of the group
-    if (gl == 0) red_add1(a.g_user_bias + x.su, cu_i + cu_j + fwd_calls * rw * x.bu);
-    if (gl == 1 % LPR) red_add1(a.g_item_bias + x.si, cu_i + rw * x.bi);
-    if (LOSS == LOSS_BPR && gl == 2 % LPR) red_add1(a.g_item_bias + x.sj, cu_j + rw * x.bj);
+    if (gl == 0) red_add1(t_gub + x.su, cu_i + cu_j + fwd_calls * rw * x.bu);
+    if (gl == 1 % LPR) red_add1(t_gib + x.si, cu_i + rw * x.bi);
+    if (LOSS == LOSS_BPR && gl == 2 % LPR) red_add1(t_gjb + x.sj, cu_j + rw * x.bj);
 }
 
 // Stage tile `t` of the batch's index lists into `dst`.  TMA path when the slice is a
@@ -227,8 +301,8 @@ __device__ __forceinline__ bool stage_tile(const MfArgs& a, long long t, IdxTile
     return used_tma;
 }
 
-template <int LPR, int VPL, bool FULL, int LOSS>
-__global__ void __launch_bounds__(kThreads, (VPL <= 2) ? 8 : 5) mf_fwd_bwd_kernel(const MfArgs a) {
+template <int LPR, int VPL, bool FULL, int LOSS, bool SHARD>
+__global__ void __launch_bounds__(kThreads, (VPL <= 2) ? 8 : (SHARD ? 4 : 5)) mf_fwd_bwd_kernel(const MfArgs a) {
     constexpr int SPW = 32 / LPR;
     __shared__ IdxTile s_tile[2];
     __shared__ __align__(8) uint64_t s_bar[2];
@@ -278,8 +352,8 @@ __global__ void __launch_bounds__(kThreads, (VPL <= 2) ? 8 : 5) mf_fwd_bwd_kerne
 
         for (int b0 = warp * SPW; b0 < tile_n; b0 += kWarps * SPW) {
             Sample<VPL, LOSS> x;
-            sample_load<LPR, VPL, FULL, LOSS>(a, T, b0 + grp, tile_n, gl, D, x);
-            sample_finish<LPR, VPL, FULL, LOSS>(a, x, gl, D, bg, loss_acc, reg_acc, gb_acc);
+            sample_load<LPR, VPL, FULL, LOSS, SHARD>(a, T, b0 + grp, tile_n, gl, D, x);
+            sample_finish<LPR, VPL, FULL, LOSS, SHARD>(a, x, gl, D, bg, loss_acc, reg_acc, gb_acc);
         }
         __syncthreads();  // everyone is done with s_tile[buf] before it is refilled
     }
@@ -354,13 +428,13 @@ int grid_for(const void* kernel, long long work_blocks) {
     return (int)(g < 1 ? 1 : g);
 }
 
-template <int LOSS>
+template <int LOSS, bool SHARD = false>
 int launch_fwd_bwd(const MfArgs& a, cudaStream_t st) {
     const int D = a.dim;
     const long long n_tiles = (a.batch + kTile - 1) / kTile;
 #define BRS_LAUNCH(LPR, VPL, FULL)                                                      \
     do {                                                                                \
-        auto k = mf_fwd_bwd_kernel<LPR, VPL, FULL, LOSS>;                               \
+        auto k = mf_fwd_bwd_kernel<LPR, VPL, FULL, LOSS, SHARD>;                        \
         k<<<grid_for((const void*)k, n_tiles), kThreads, 0, st>>>(a);                   \
     } while (0)
     if (D % 4 != 0 || D <= 0 || D > 512) return BRS_ERR_UNSUPPORTED;
@@ -422,6 +496,10 @@ int fill_args(const brs_mf_model* m, MfArgs& a, bool need_grad) {
     }
     a.user_slot = m->user.rows.slot_map;
     a.item_slot = m->item.rows.slot_map;
+    a.user_cap = m->user.rows.capacity;
+    a.item_cap = m->item.rows.capacity;
+    a.peers = nullptr;
+    a.shard_shift = a.shard_mask = 0;
     a.ws = (brs_step_ws*)m->ws;
     a.n_users = m->user.table[0].n_rows;
     a.n_items = m->item.table[0].n_rows;

@@ -42,6 +42,7 @@ struct NcfArgs {
     const float* u_mlp; const float* i_mlp; const float* u_mf; const float* i_mf;
     float* g_u_mlp; float* g_i_mlp; float* g_u_mf; float* g_i_mf;  // compact scratch, indexed by slot
     const int* user_slot; const int* item_slot;                      // slot maps filled by the pre-pass
+    int user_cap, item_cap;                                          // scratch capacities (gs_off layout)
     long long n_users, n_items;
     const long long* users; const long long* items; const float* ratings;
     long long batch;
@@ -213,8 +214,8 @@ __global__ void __launch_bounds__(kThreads) ncf_scatter_kernel(const NcfArgs a) 
         if (a.mlp_dim) {
             const float* d = a.dx0 + s * 2 * a.mlp_dim;
             for (int c = lane * 4; c < a.mlp_dim; c += 128) {
-                red_add4(a.g_u_mlp + su * a.mlp_dim + c, *(const float4*)(d + c));
-                red_add4(a.g_i_mlp + si * a.mlp_dim + c, *(const float4*)(d + a.mlp_dim + c));
+                red_add4(a.g_u_mlp + gs_off(a.mlp_dim, a.user_cap, (unsigned)su, c), *(const float4*)(d + c));
+                red_add4(a.g_i_mlp + gs_off(a.mlp_dim, a.item_cap, (unsigned)si, c), *(const float4*)(d + a.mlp_dim + c));
             }
         }
         if (a.kind == BRS_NCF_NEUMF) {
@@ -223,8 +224,8 @@ __global__ void __launch_bounds__(kThreads) ncf_scatter_kernel(const NcfArgs a) 
                 const float4 w = *(const float4*)(a.w_out + H + c);
                 const float4 uf = ld_row4(a.u_mf + u * a.mf_dim + c);
                 const float4 jf = ld_row4(a.i_mf + i * a.mf_dim + c);
-                red_add4(a.g_u_mf + su * a.mf_dim + c, make_float4(dz * w.x * jf.x, dz * w.y * jf.y, dz * w.z * jf.z, dz * w.w * jf.w));
-                red_add4(a.g_i_mf + si * a.mf_dim + c, make_float4(dz * w.x * uf.x, dz * w.y * uf.y, dz * w.z * uf.z, dz * w.w * uf.w));
+                red_add4(a.g_u_mf + gs_off(a.mf_dim, a.user_cap, (unsigned)su, c), make_float4(dz * w.x * jf.x, dz * w.y * jf.y, dz * w.z * jf.z, dz * w.w * jf.w));
+                red_add4(a.g_i_mf + gs_off(a.mf_dim, a.item_cap, (unsigned)si, c), make_float4(dz * w.x * uf.x, dz * w.y * uf.y, dz * w.z * uf.z, dz * w.w * uf.w));
             }
         }
     }
@@ -284,9 +285,9 @@ __global__ void __launch_bounds__(kThreads) gmf_fused_kernel(const NcfArgs a) {
             if (c < E) {
                 const float4 p = make_float4(uf[v].x * jf[v].x, uf[v].y * jf[v].y, uf[v].z * jf[v].z, uf[v].w * jf[v].w);
                 gw[v].x += dz * p.x; gw[v].y += dz * p.y; gw[v].z += dz * p.z; gw[v].w += dz * p.w;
-                red_add4(a.g_u_mf + su * E + c, make_float4(dz * wv[v].x * jf[v].x, dz * wv[v].y * jf[v].y,
+                red_add4(a.g_u_mf + gs_off(E, a.user_cap, (unsigned)su, c), make_float4(dz * wv[v].x * jf[v].x, dz * wv[v].y * jf[v].y,
                                                            dz * wv[v].z * jf[v].z, dz * wv[v].w * jf[v].w));
-                red_add4(a.g_i_mf + si * E + c, make_float4(dz * wv[v].x * uf[v].x, dz * wv[v].y * uf[v].y,
+                red_add4(a.g_i_mf + gs_off(E, a.item_cap, (unsigned)si, c), make_float4(dz * wv[v].x * uf[v].x, dz * wv[v].y * uf[v].y,
                                                            dz * wv[v].z * uf[v].z, dz * wv[v].w * uf[v].w));
             }
         }
@@ -357,6 +358,8 @@ void fill(const brs_ncf_model* m, NcfArgs& a) {
     a.n_items = m->item.table[0].n_rows;
     a.user_slot = m->user.rows.slot_map;
     a.item_slot = m->item.rows.slot_map;
+    a.user_cap = m->user.rows.capacity;
+    a.item_cap = m->item.rows.capacity;
     a.ws = (brs_step_ws*)m->ws;
     a.w_out = m->out_weight.weight;
     a.b_out = m->out_bias.weight;

@@ -166,16 +166,17 @@ struct ApplyArgs {
 
 // one touched row of one table: scratch row `slot` -> weight row `row`
 template <int KIND>
-__device__ __forceinline__ void update_row(const brs_table& tb, long long row, long long slot, int lane,
+__device__ __forceinline__ void update_row(const brs_table& tb, int cap, long long row, long long slot, int lane,
                                            const OptScalars& s) {
     const int d = tb.dim;
     float* w = tb.weight + row * d;
-    float* g = tb.grad + slot * d;
+    float* g = tb.grad;  // addressed through gs_off (sector-blocked when d % 8 == 0)
     float* m = (KIND == BRS_ADAM) ? tb.m + row * d : nullptr;
     float* v = (KIND != BRS_SGD) ? tb.v + row * d : nullptr;
     if ((d & 3) == 0) {
         for (int c = lane * 4; c < d; c += 128) {
-            float4 gv = *(const float4*)(g + c);
+            float4* gp = (float4*)(g + gs_off(d, cap, (unsigned)slot, c));
+            float4 gv = *gp;
             float4 wv = *(const float4*)(w + c);
             float4 mv = make_float4(0.f, 0.f, 0.f, 0.f), vv = mv;
             if (KIND == BRS_ADAM) mv = *(const float4*)(m + c);
@@ -184,9 +185,10 @@ __device__ __forceinline__ void update_row(const brs_table& tb, long long row, l
             *(float4*)(w + c) = wv;
             if (KIND == BRS_ADAM) *(float4*)(m + c) = mv;
             if (KIND != BRS_SGD) *(float4*)(v + c) = vv;
-            *(float4*)(g + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+            *gp = make_float4(0.f, 0.f, 0.f, 0.f);
         }
     } else {
+        g += (size_t)slot * d;  // row-major for dims that are not multiples of 8
         for (int c = lane; c < d; c += 32) {
             float gv = g[c], wv = w[c];
             float mv = (KIND == BRS_ADAM) ? m[c] : 0.f;
@@ -203,8 +205,8 @@ __device__ __forceinline__ void update_row(const brs_table& tb, long long row, l
 // fast path: ROWS touched rows of a (dim % 4 == 0, dim <= 128) table in flight per warp.
 // SGD needs no weight load at all: w += -lr*g leaves as a fire-and-forget 128-bit RED.
 template <int KIND, int ROWS>
-__device__ __forceinline__ void update_rows_small(const brs_table& tb, const int (&row)[ROWS], int s0, int n, int lane,
-                                                  const OptScalars& s) {
+__device__ __forceinline__ void update_rows_small(const brs_table& tb, int cap, const int (&row)[ROWS], int s0, int n,
+                                                  int lane, const OptScalars& s) {
     const int d = tb.dim, c = lane * 4;
     if (c >= d) return;
     float4 gv[ROWS], wv[ROWS], mv[ROWS], vv[ROWS];
@@ -213,7 +215,7 @@ __device__ __forceinline__ void update_rows_small(const brs_table& tb, const int
         wv[r] = mv[r] = vv[r] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (r < n) {
             const size_t ro = (size_t)(unsigned)row[r] * (unsigned)d + c;
-            gv[r] = *(const float4*)(tb.grad + (size_t)(unsigned)(s0 + r) * (unsigned)d + c);
+            gv[r] = *(const float4*)(tb.grad + gs_off(d, cap, (unsigned)(s0 + r), c));
             if (KIND != BRS_SGD) wv[r] = *(const float4*)(tb.weight + ro);
             if (KIND == BRS_ADAM) mv[r] = *(const float4*)(tb.m + ro);
             if (KIND != BRS_SGD) vv[r] = *(const float4*)(tb.v + ro);
@@ -231,7 +233,7 @@ __device__ __forceinline__ void update_rows_small(const brs_table& tb, const int
                 if (KIND == BRS_ADAM) *(float4*)(tb.m + ro) = mv[r];
                 *(float4*)(tb.v + ro) = vv[r];
             }
-            *(float4*)(tb.grad + (size_t)(unsigned)(s0 + r) * (unsigned)d + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+            *(float4*)(tb.grad + gs_off(d, cap, (unsigned)(s0 + r), c)) = make_float4(0.f, 0.f, 0.f, 0.f);
         }
     }
 }
@@ -347,13 +349,13 @@ __global__ void __launch_bounds__(kThreads) rows_apply_kernel(const ApplyArgs a)
         for (int k = 0; k < en.n_tables; ++k) {
             const brs_table& tb = en.table[k];
             if ((tb.dim & 3) == 0 && tb.dim <= 128) {
-                update_rows_small<KIND, ROWS>(tb, row, s0, n, lane, s);
+                update_rows_small<KIND, ROWS>(tb, en.rows.capacity, row, s0, n, lane, s);
             } else if (tb.dim == 1) {  // bias tables: lane q handles row q
-                if (lane < n) update_row<KIND>(tb, my_row, s0 + lane, 0, s);
+                if (lane < n) update_row<KIND>(tb, en.rows.capacity, my_row, s0 + lane, 0, s);
             } else {
 #pragma unroll
                 for (int q = 0; q < ROWS; ++q)
-                    if (q < n) update_row<KIND>(tb, row[q], s0 + q, lane, s);
+                    if (q < n) update_row<KIND>(tb, en.rows.capacity, row[q], s0 + q, lane, s);
             }
         }
         if (lane < n) en.rows.slot_map[my_row] = BRS_SLOT_NONE;  // release the slot
@@ -370,8 +372,8 @@ __global__ void __launch_bounds__(kThreads) rows_apply_kernel(const ApplyArgs a)
 // ---- every row (reference-exact Adam / RMSprop) -----------------------------
 // grid-stride over float4 vectors (or scalars when dim % 4 != 0) of one table
 template <int KIND>
-__device__ __forceinline__ void sweep_table(const brs_table& tb, const int* __restrict__ slot_map, const OptScalars& s,
-                                            long long tid, long long nthreads) {
+__device__ __forceinline__ void sweep_table(const brs_table& tb, const int* __restrict__ slot_map, int cap,
+                                            const OptScalars& s, long long tid, long long nthreads) {
     const int d = tb.dim;
     if ((d & 3) == 0) {
         const int vpr = d >> 2;
@@ -382,7 +384,7 @@ __device__ __forceinline__ void sweep_table(const brs_table& tb, const int* __re
             const int slot = slot_map[row];
             float4 gv = make_float4(0.f, 0.f, 0.f, 0.f);
             if (slot >= 0) {
-                float4* gp = (float4*)(tb.grad + (long long)slot * d) + (i - row * vpr);
+                float4* gp = (float4*)(tb.grad + gs_off(d, cap, (unsigned)slot, (int)(i - row * vpr) * 4));
                 gv = *gp;
                 *gp = make_float4(0.f, 0.f, 0.f, 0.f);
             }
@@ -427,7 +429,7 @@ __global__ void __launch_bounds__(kThreads) dense_sweep_kernel(const ApplyArgs a
     const long long nthreads = (long long)gridDim.x * kThreads;
     for (int e = 0; e < a.n_ent; ++e)
         for (int k = 0; k < a.ent[e].n_tables; ++k)
-            sweep_table<KIND>(a.ent[e].table[k], a.ent[e].rows.slot_map, s, tid, nthreads);
+            sweep_table<KIND>(a.ent[e].table[k], a.ent[e].rows.slot_map, a.ent[e].rows.capacity, s, tid, nthreads);
     dense_params_update<KIND>(a, s);
     if (a.ws) {
         if (last_block(a)) finalize<KIND>(a, s);
@@ -516,8 +518,9 @@ int launch_apply(const ApplyArgs& a, int mode, long long max_rows_hint, cudaStre
 
 // grad_scratch[slot_map[idx[k]]] += scale * src[k]: the scatter half of an embedding backward
 __global__ void __launch_bounds__(kThreads) rows_scatter_grad_kernel(brs_table tb, const int* __restrict__ slot_map,
-                                                                     const long long* __restrict__ idx, long long n,
-                                                                     const float* __restrict__ src, float scale) {
+                                                                     int cap, const long long* __restrict__ idx,
+                                                                     long long n, const float* __restrict__ src,
+                                                                     float scale) {
     const int lane = threadIdx.x & 31;
     const int d = tb.dim;
     for (long long k = (long long)blockIdx.x * kWarps + (threadIdx.x >> 5); k < n; k += (long long)gridDim.x * kWarps) {
@@ -525,15 +528,14 @@ __global__ void __launch_bounds__(kThreads) rows_scatter_grad_kernel(brs_table t
         if ((unsigned long long)row >= (unsigned long long)tb.n_rows) continue;
         const long long slot = slot_map[row];
         if (slot < 0) continue;
-        float* g = tb.grad + slot * d;
         const float* sp = src + k * d;
         if ((d & 3) == 0) {
             for (int c = lane * 4; c < d; c += 128) {
                 const float4 x = *(const float4*)(sp + c);
-                red_add4(g + c, make_float4(scale * x.x, scale * x.y, scale * x.z, scale * x.w));
+                red_add4(tb.grad + gs_off(d, cap, (unsigned)slot, c), make_float4(scale * x.x, scale * x.y, scale * x.z, scale * x.w));
             }
         } else {
-            for (int c = lane; c < d; c += 32) red_add1(g + c, scale * sp[c]);
+            for (int c = lane; c < d; c += 32) red_add1(tb.grad + slot * d + c, scale * sp[c]);
         }
     }
 }
@@ -556,8 +558,8 @@ extern "C" int brs_rows_scatter_grad(const brs_entity* entity, int32_t table, co
     long long blocks = (n + kWarps - 1) / kWarps;
     const long long cap = (long long)brs_sm_count() * 8;
     if (blocks > cap) blocks = cap;
-    rows_scatter_grad_kernel<<<(int)blocks, kThreads, 0, (cudaStream_t)stream>>>(tb, entity->rows.slot_map,
-                                                                                 (const long long*)idx, n, src, scale);
+    rows_scatter_grad_kernel<<<(int)blocks, kThreads, 0, (cudaStream_t)stream>>>(
+        tb, entity->rows.slot_map, entity->rows.capacity, (const long long*)idx, n, src, scale);
     BRS_CUDA_CHECK(cudaGetLastError());
     return BRS_OK;
 }

@@ -21,6 +21,9 @@ class _NullWriter(object):
     def add_scalars(self, *a, **k):
         pass
 
+    def add_text(self, *a, **k):
+        pass
+
     def close(self):
         pass
 

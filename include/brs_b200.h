@@ -66,10 +66,13 @@ typedef struct brs_opt {
 /* ---- one embedding table + its per-step gradient scratch and optimizer state ---- */
 typedef struct brs_table {
     float *weight;   /* [n_rows, dim] row-major; 16-byte aligned when dim % 4 == 0 */
-    float *grad;     /* [rowset.capacity, dim] COMPACT gradient scratch: row s holds the summed gradient of
+    float *grad;     /* capacity*dim floats of COMPACT gradient scratch: slot s holds the summed gradient of
                         table row rowset.list[s]; all-zero between steps.  The same few tens of MB are
                         reused every step, so the scatter-add stays in L2 instead of touching a
-                        table-sized dense gradient (what autograd materialises in the reference). */
+                        table-sized dense gradient (what autograd materialises in the reference).
+                        Layout: row-major [capacity][dim], EXCEPT when dim % 8 == 0, where it is
+                        sector-blocked [dim/8][capacity][8]: element (s, c) at ((c>>3)*capacity + s)*8 + (c&7),
+                        so one row's 32-byte sectors land on different L2 slices (RED throughput). */
     float *m;        /* Adam exp_avg            (NULL for SGD / RMSprop) */
     float *v;        /* Adam exp_avg_sq / RMSprop square_avg (NULL for SGD) */
     int64_t n_rows;
@@ -122,6 +125,14 @@ typedef struct brs_mf_model {
     brs_dense_param global_bias;  /* numel 1 */
     void *ws;                     /* BRS_STEP_WS_BYTES of device scratch */
 } brs_mf_model;
+
+/* one rank's MF shard as seen from the calling process (pointers mapped through CUDA IPC / NVLink peer
+ * access); a device-resident array of these, indexed by rank, drives the row-sharded kernels */
+typedef struct brs_mf_peer_tables {
+    const float *user_emb, *item_emb, *user_bias, *item_bias;
+    float *g_user_emb, *g_item_emb, *g_user_bias, *g_item_bias;
+    const int32_t *user_slot, *item_slot;
+} brs_mf_peer_tables;
 
 /* library / device */
 int brs_abi_version(void);

@@ -69,6 +69,9 @@ def install():
         def add_scalars(self, *a, **k):
             pass
 
+        def add_text(self, *a, **k):
+            pass
+
         def close(self):
             pass
 
@@ -79,6 +82,7 @@ def install():
     ray = stub("ray")
     tune = stub("ray.tune", grid_search=lambda v: v, report=lambda **k: None)
     ray.tune = tune
+    ray.utils = stub("ray.utils")  # train_engine.py:156 assigns ray.utils.get_user_temp_dir
     import unittest.mock as _um
 
     sys.modules.setdefault("mock", _um)
