@@ -63,7 +63,28 @@ class NcfModel(C.Structure):
                 ("mfv", C.c_void_p), ("dz", C.c_void_p), ("max_batch", C.c_int64), ("ws", C.c_void_p)]
 
 
-EXTRA_STRUCTS = {"brs_ncf_model": NcfModel}
+MAX_RANKS = 8
+IPC_HANDLE_BYTES = 64
+
+
+class MfPeerTables(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "user_emb", "item_emb", "user_bias", "item_bias", "g_user_emb", "g_item_emb", "g_user_bias", "g_item_bias",
+        "user_slot", "item_slot", "user_list", "item_list", "user_count", "item_count")]
+
+
+class PeerSync(C.Structure):
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("flags", C.c_void_p * MAX_RANKS),
+                ("partials", C.c_void_p * MAX_RANKS)]
+
+
+class MfSharded(C.Structure):
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("n_users", C.c_int64), ("n_items", C.c_int64),
+                ("local", MfModel), ("peers", C.c_void_p)]
+
+
+EXTRA_STRUCTS = {"brs_ncf_model": NcfModel, "brs_mf_peer_tables": MfPeerTables, "brs_peer_sync": PeerSync,
+                 "brs_mf_sharded": MfSharded}
 
 _P = C.c_void_p
 _PROTOTYPES = {
@@ -94,6 +115,14 @@ _PROTOTYPES = {
     "brs_rows_adam": (C.c_int, [C.POINTER(Entity), C.c_int32, C.POINTER(Opt), C.c_int64, _P]),
     "brs_dense_adam_sweep": (C.c_int, [C.POINTER(Entity), C.c_int32, C.POINTER(Opt), C.c_int64, _P]),
     "brs_dense_params_step": (C.c_int, [C.POINTER(DenseParam), C.c_int32, C.POINTER(Opt), C.c_int64, _P]),
+    "brs_shm_alloc": (C.c_int, [C.c_int64, C.POINTER(C.c_void_p)]),
+    "brs_shm_free": (C.c_int, [_P]),
+    "brs_ipc_get_handle": (C.c_int, [_P, C.POINTER(C.c_uint8)]),
+    "brs_ipc_open_handle": (C.c_int, [C.POINTER(C.c_uint8), C.POINTER(C.c_void_p)]),
+    "brs_ipc_close_handle": (C.c_int, [_P]),
+    "brs_peer_barrier": (C.c_int, [C.POINTER(PeerSync), C.c_uint64, _P, _P]),
+    "brs_mf_sharded_bpr_fwd_bwd": (C.c_int, [C.POINTER(MfSharded), _P, _P, _P, C.c_int64, C.c_int64, C.c_float, _P]),
+    "brs_route_triples": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, _P, _P, _P, _P, _P]),
     "brs_gather": (C.c_int, [_P, C.c_int64, C.c_int32, _P, C.c_int64, _P, _P]),
     "brs_scatter_add": (C.c_int, [_P, C.c_int64, C.c_int32, _P, C.c_int64, _P, C.c_float, _P]),
     "brs_gather_sgd_update": (C.c_int, [_P, C.c_int64, C.c_int32, _P, C.c_int64, C.c_float, _P, _P]),

@@ -26,6 +26,9 @@
 
 int brs_assign_slots(const brs_rowset* rs, const long long* const* idx, const long long* n, int n_arrays,
                      brs_step_ws* ws, cudaStream_t st);
+int brs_assign_slots_sharded(const brs_mf_peer_tables* peers, int world_shift, int user_cap, int item_cap,
+                             long long n_users, long long n_items, const long long* users, const long long* pos,
+                             const long long* neg, long long n, brs_step_ws* ws, cudaStream_t st);
 
 namespace {
 
@@ -44,8 +47,12 @@ struct MfPeerTables {  // one rank's shard, as seen from this process (device-re
     float* g_item_emb;
     float* g_user_bias;
     float* g_item_bias;
-    const int* user_slot;
-    const int* item_slot;
+    int* user_slot;
+    int* item_slot;
+    int* user_list;
+    int* item_list;
+    int* user_count;
+    int* item_count;
 };
 static_assert(sizeof(MfPeerTables) == sizeof(brs_mf_peer_tables), "peer table layout is part of the ABI");
 
@@ -603,4 +610,35 @@ extern "C" int brs_mf_predict(const brs_mf_model* model, const int64_t* users, c
 #undef BRS_PRED
     BRS_CUDA_CHECK(cudaGetLastError());
     return BRS_OK;
+}
+
+extern "C" int brs_mf_sharded_bpr_fwd_bwd(const brs_mf_sharded* model, const int64_t* users, const int64_t* pos_items,
+                                          const int64_t* neg_items, int64_t batch, int64_t global_batch,
+                                          float reg_weight, void* stream) {
+    if (!model || !model->peers || !users || !pos_items || !neg_items || batch < 0 || global_batch < batch)
+        return BRS_ERR_INVALID_ARG;
+    const int w = model->world;
+    if (w < 1 || w > BRS_MAX_RANKS || (w & (w - 1)) != 0 || model->rank < 0 || model->rank >= w) return BRS_ERR_UNSUPPORTED;
+    MfArgs a;
+    int rc = fill_args(&model->local, a, true);
+    if (rc != BRS_OK) return rc;
+    if (batch == 0) return BRS_OK;
+    int shift = 0;
+    while ((1 << shift) < w) ++shift;
+    a.n_users = model->n_users;  // GLOBAL ids are range-checked against the global sizes
+    a.n_items = model->n_items;
+    a.peers = (const MfPeerTables*)model->peers;
+    a.shard_shift = shift;
+    a.shard_mask = w - 1;
+    a.users = (const long long*)users;
+    a.items = (const long long*)pos_items;
+    a.third = neg_items;
+    a.batch = batch;
+    a.reg_w = reg_weight;
+    a.inv_b = 1.0f / (float)global_batch;
+    cudaStream_t st = (cudaStream_t)stream;
+    rc = brs_assign_slots_sharded(model->peers, shift, a.user_cap, a.item_cap, model->n_users, model->n_items,
+                                  a.users, a.items, (const long long*)neg_items, batch, a.ws, st);
+    if (rc != BRS_OK) return rc;
+    return launch_fwd_bwd<LOSS_BPR, true>(a, st);
 }

@@ -1,0 +1,342 @@
+"""Row-sharded multi-GPU MF engine (one process per GPU, torch.distributed for plumbing).
+
+New work -- the reference has no distributed path.  Tables are
+row-sharded: ``owner(row) = row mod world``, ``local row = row div world``.  Every rank
+exports its shard (tables, compact gradient scratch, slot maps) through CUDA IPC; the
+kernels then address remote rows directly over NVLink: gathers are peer loads, gradient
+scatters are peer REDs into the owner's scratch, slots are claimed with peer atomics.
+A step is
+
+    [optional NCCL all-to-all: route triples to the user-row owner]
+    slot pre-pass + fused fwd/bwd   (peer memory, no collective)
+    flag barrier  (+ exchange of the 3 step sums, added in rank order)
+    optimizer on the local shard     (global_bias is replicated and updated identically)
+    flag barrier
+
+The loss is the mean over the GLOBAL batch (sum of the ranks' batches), exactly what a
+single-GPU run on the concatenated batch computes.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from .engines.rows import as_index
+
+
+# --------------------------------------------------------------------------- #
+# host-side index rules (pure functions; covered by the CPU tests)
+# --------------------------------------------------------------------------- #
+def owner_of(rows, world):
+    """(owner rank, local row) of global row ids under the interleaved sharding."""
+    return rows % world, rows // world
+
+
+def local_rows(n_rows, world):
+    """Rows every rank reserves for a table of n_rows global rows (uniform, ceil)."""
+    return (int(n_rows) + world - 1) // world
+
+
+def shard_of(full, world, rank):
+    """Rows of a full [N, ...] array owned by `rank`, padded to local_rows(N, world)."""
+    part = full[rank::world]
+    need = local_rows(full.shape[0], world)
+    if part.shape[0] < need:
+        pad = np.zeros((need - part.shape[0],) + full.shape[1:], dtype=full.dtype)
+        part = np.concatenate([part, pad], axis=0)
+    return np.ascontiguousarray(part)
+
+
+def unshard(parts, n_rows):
+    """Inverse of shard_of over all ranks: parts[r] is rank r's [local_rows, ...] array."""
+    world = len(parts)
+    out = np.zeros((n_rows,) + parts[0].shape[1:], dtype=parts[0].dtype)
+    for r, p in enumerate(parts):
+        cnt = (n_rows - r + world - 1) // world
+        out[r::world] = p[:cnt]
+    return out
+
+
+def all_to_all_v(send, send_counts, group=None):
+    """Variable-size all-to-all of a 1-D/2-D tensor whose dim 0 is grouped by destination.
+    NCCL: one all_to_all_single; other backends (gloo in the CPU tests): point-to-point."""
+    world = dist.get_world_size(group)
+    sc = torch.as_tensor(send_counts, dtype=torch.int64)
+    rc = torch.empty(world, dtype=torch.int64)
+    if dist.get_backend(group) == "nccl":
+        sc_d, rc_d = sc.to(send.device), torch.empty(world, dtype=torch.int64, device=send.device)
+        dist.all_to_all_single(rc_d, sc_d, group=group)
+        rc = rc_d.cpu()
+    else:
+        gathered = [torch.empty(world, dtype=torch.int64) for _ in range(world)]
+        dist.all_gather(gathered, sc, group=group)
+        me = dist.get_rank(group)
+        rc = torch.stack([g[me] for g in gathered])
+    recv = send.new_empty((int(rc.sum()),) + tuple(send.shape[1:]))
+    if dist.get_backend(group) == "nccl":
+        dist.all_to_all_single(recv, send, rc.tolist(), sc.tolist(), group=group)
+    else:
+        me = dist.get_rank(group)
+        so = np.concatenate([[0], np.cumsum(sc.numpy())])
+        ro = np.concatenate([[0], np.cumsum(rc.numpy())])
+        reqs = []
+        for r in range(world):
+            if r == me:
+                recv[ro[r]:ro[r + 1]] = send[so[r]:so[r + 1]]
+                continue
+            reqs.append(dist.isend(send[so[r]:so[r + 1]].contiguous(), r, group=group))
+            reqs.append(dist.irecv(recv[ro[r]:ro[r + 1]], r, group=group))
+        for q in reqs:
+            q.wait()
+    return recv, rc.tolist()
+
+
+# --------------------------------------------------------------------------- #
+# exportable device memory
+# --------------------------------------------------------------------------- #
+class _Raw(object):
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3}
+
+
+class PeerArena(object):
+    """One cudaMalloc'ed, IPC-exported block per rank with the SAME named layout on every
+    rank, so that (peer base + offset[name]) addresses any peer's buffer."""
+
+    ALIGN = 256
+
+    def __init__(self, layout, device, group=None):
+        lib = _lib.load()
+        self.group = group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.device = device
+        self.offsets, self.specs, off = {}, {}, 0
+        for name, shape, dtype in layout:
+            nbytes = int(np.prod(shape)) * torch.empty((), dtype=dtype).element_size()
+            self.offsets[name] = off
+            self.specs[name] = (tuple(int(x) for x in shape), dtype, nbytes)
+            off += (nbytes + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        self.nbytes = max(off, self.ALIGN)
+        base = C.c_void_p()
+        with torch.cuda.device(device):
+            _lib.check(lib.brs_shm_alloc(self.nbytes, C.byref(base)), "brs_shm_alloc")
+            self.base = base.value
+            self._raw = torch.as_tensor(_Raw(self.base, self.nbytes), device=device)
+            handle = (C.c_uint8 * _lib.IPC_HANDLE_BYTES)()
+            _lib.check(lib.brs_ipc_get_handle(self.base, handle), "brs_ipc_get_handle")
+            handles = [None] * self.world
+            dist.all_gather_object(handles, bytes(handle), group=group)
+            self.peer_base = []
+            for r, h in enumerate(handles):
+                if r == self.rank:
+                    self.peer_base.append(self.base)
+                    continue
+                buf = (C.c_uint8 * _lib.IPC_HANDLE_BYTES).from_buffer_copy(h)
+                p = C.c_void_p()
+                _lib.check(lib.brs_ipc_open_handle(buf, C.byref(p)), "brs_ipc_open_handle")
+                self.peer_base.append(p.value)
+
+    def tensor(self, name):
+        shape, dtype, nbytes = self.specs[name]
+        o = self.offsets[name]
+        return self._raw[o:o + nbytes].view(dtype).view(shape)
+
+    def ptr(self, name, rank=None):
+        return (self.peer_base[self.rank if rank is None else rank]) + self.offsets[name]
+
+    def close(self):
+        lib = _lib.load()
+        dist.barrier(group=self.group)  # nobody may still be reading our memory
+        for r, p in enumerate(self.peer_base):
+            if r != self.rank and p:
+                lib.brs_ipc_close_handle(p)
+        self.peer_base = []
+        self._raw = None
+        if self.base:
+            lib.brs_shm_free(self.base)
+            self.base = None
+
+
+# --------------------------------------------------------------------------- #
+# the engine
+# --------------------------------------------------------------------------- #
+class ShardedMFEngine(object):
+    """MF-BPR over row-sharded tables.  ``config["model"]`` as for MFEngine (GLOBAL
+    n_users / n_items; batch_size is PER RANK); ``route`` = "none" (default: every rank
+    trains its own triples, all rows through peer memory) or "owner" (NCCL all-to-all
+    routes each triple to the rank that owns its user row first)."""
+
+    def __init__(self, config, group=None, route="none", state=None):
+        if not dist.is_initialized():
+            raise _lib.BrsError("ShardedMFEngine needs an initialised torch.distributed process group")
+        m = config["model"]
+        self.config, self.group, self.route = config, group, route
+        if route not in ("none", "owner"):
+            raise ValueError("route must be 'none' or 'owner'")
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world > _lib.MAX_RANKS or self.world & (self.world - 1):
+            raise _lib.BrsError("world size must be a power of two <= %d" % _lib.MAX_RANKS)
+        self.device = torch.device(m["device_str"])
+        if self.device.type != "cuda":
+            raise _lib.BrsError("ShardedMFEngine runs on CUDA devices only (no CPU fallback)")
+        self.lib = _lib.load()
+        self.n_users, self.n_items, self.dim = int(m["n_users"]), int(m["n_items"]), int(m["emb_dim"])
+        self.batch_size = int(m["batch_size"])
+        self.reg = config["model"]["reg"] if "reg" in config else 0.0  # mf.py:81-83 quirk
+        if (m["loss"] if "loss" in m else "bpr") != "bpr":
+            raise _lib.BrsError("ShardedMFEngine implements the BPR loss")
+        self.opt_kind, self.lr = m["optimizer"], float(m["lr"])
+        mode = m["adam_mode"] if "adam_mode" in m else "dense"
+        self.opt = _lib.make_opt(self.opt_kind, self.lr, _lib.DENSE if mode == "dense" else _lib.TOUCHED_ROWS)
+        w, d = self.world, self.dim
+        lu, li = local_rows(self.n_users, w), local_rows(self.n_items, w)
+        # a slot for every distinct row any rank can send here in one step
+        grow = 2 if route == "owner" else 1  # routed batches are uneven (Zipf users)
+        self.cap_u = int(max(1, min(lu, grow * w * self.batch_size)))
+        self.cap_i = int(max(1, min(li, 2 * grow * w * self.batch_size)))
+        f32, i32 = torch.float32, torch.int32
+        layout = [
+            ("user_emb", (lu, d), f32), ("item_emb", (li, d), f32), ("user_bias", (lu, 1), f32),
+            ("item_bias", (li, 1), f32), ("g_user_emb", (self.cap_u * d,), f32), ("g_item_emb", (self.cap_i * d,), f32),
+            ("g_user_bias", (self.cap_u,), f32), ("g_item_bias", (self.cap_i,), f32), ("user_slot", (lu,), i32),
+            ("item_slot", (li,), i32), ("user_list", (self.cap_u,), i32), ("item_list", (self.cap_i,), i32),
+            ("user_count", (1,), i32), ("item_count", (1,), i32), ("flags", (_lib.MAX_RANKS,), torch.int64),
+            ("partials", (_lib.MAX_RANKS * 4,), torch.float64), ("ws", (_lib.STEP_WS_BYTES,), torch.uint8),
+        ]
+        self.arena = PeerArena(layout, self.device, group)
+        t = self.arena.tensor
+        t("user_slot").fill_(-1)
+        t("item_slot").fill_(-1)
+        self.global_bias = torch.zeros(1, dtype=f32, device=self.device)  # replicated
+        self._init_tables(state)
+        # optimizer state: local only
+        self.state = {}
+        for name in ("user_emb", "item_emb", "user_bias", "item_bias"):
+            self.state[name] = self._new_state(t(name))
+        self.state["global_bias"] = self._new_state(self.global_bias)
+        self._out = torch.zeros(4, dtype=f32, device=self.device)
+        self._epoch = 0
+        self._build_structs()
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=group)
+
+    # -- construction helpers ------------------------------------------------ #
+    def _new_state(self, tensor):
+        st = {}
+        if self.opt_kind == "adam":
+            st["m"] = torch.zeros_like(tensor)
+        if self.opt_kind in ("adam", "rmsprop"):
+            st["v"] = torch.zeros_like(tensor)
+        return st
+
+    def _init_tables(self, state):
+        """state: full (unsharded) numpy state dict with the reference keys, or None for
+        MF's own init (N(0, 0.1^2) embeddings, zero biases; mf.py:25-30) seeded per rank."""
+        t = self.arena.tensor
+        if state is not None:
+            for name, key in (("user_emb", "user_emb.weight"), ("item_emb", "item_emb.weight"),
+                              ("user_bias", "user_bias.weight"), ("item_bias", "item_bias.weight")):
+                t(name).copy_(torch.from_numpy(shard_of(np.asarray(state[key], dtype=np.float32), self.world, self.rank)))
+            self.global_bias.copy_(torch.from_numpy(np.asarray(state["global_bias"], dtype=np.float32)))
+        else:
+            g = torch.Generator(device=self.device)
+            g.manual_seed(2020 + self.rank)
+            t("user_emb").normal_(0, 0.1, generator=g)
+            t("item_emb").normal_(0, 0.1, generator=g)
+
+    def _build_structs(self):
+        A = self.arena
+        w, d = self.world, self.dim
+        lu, li = local_rows(self.n_users, w), local_rows(self.n_items, w)
+
+        def table(name, gname, rows, dim):
+            st = self.state[name]
+            return _lib.Table(A.ptr(name), A.ptr(gname), _lib.ptr(st.get("m")), _lib.ptr(st.get("v")), rows, dim, 0)
+
+        def entity(prefix, rows, cap):
+            e = _lib.Entity()
+            e.rows = _lib.Rowset(A.ptr(prefix + "_slot"), A.ptr(prefix + "_list"), A.ptr(prefix + "_count"), rows, cap, 0)
+            e.n_tables = 2
+            e.table[0] = table(prefix + "_emb", "g_" + prefix + "_emb", rows, d)
+            e.table[1] = table(prefix + "_bias", "g_" + prefix + "_bias", rows, 1)
+            return e
+
+        gb = self.state["global_bias"]
+        local = _lib.MfModel(entity("user", lu, self.cap_u), entity("item", li, self.cap_i),
+                             _lib.DenseParam(_lib.ptr(self.global_bias), None, _lib.ptr(gb.get("m")),
+                                             _lib.ptr(gb.get("v")), 1), A.ptr("ws"))
+        peers = (_lib.MfPeerTables * w)()
+        for r in range(w):
+            for f, _ in _lib.MfPeerTables._fields_:
+                setattr(peers[r], f, A.ptr(f, r))
+        self._peers_dev = torch.frombuffer(bytearray(bytes(peers)), dtype=torch.uint8).to(self.device)
+        self._cmodel = _lib.MfSharded(w, self.rank, self.n_users, self.n_items, local, self._peers_dev.data_ptr())
+        self._sync = _lib.PeerSync()
+        self._sync.world, self._sync.rank = w, self.rank
+        for r in range(w):
+            self._sync.flags[r] = A.ptr("flags", r)
+            self._sync.partials[r] = A.ptr("partials", r)
+
+    # -- step ---------------------------------------------------------------- #
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _barrier(self, with_sums):
+        self._epoch += 1
+        _lib.check(self.lib.brs_peer_barrier(C.byref(self._sync), self._epoch,
+                                             self.arena.ptr("ws") if with_sums else None, self._stream()),
+                   "brs_peer_barrier")
+
+    def route_triples(self, users, pos, neg):
+        """NCCL all-to-all of triples to the rank owning the user row (north-star routing)."""
+        n = users.numel()
+        ou, op_, on = torch.empty_like(users), torch.empty_like(pos), torch.empty_like(neg)
+        counts = torch.empty(self.world, dtype=torch.int64, device=self.device)
+        _lib.check(self.lib.brs_route_triples(_lib.ptr(users), _lib.ptr(pos), _lib.ptr(neg), n, self.world,
+                                              _lib.ptr(ou), _lib.ptr(op_), _lib.ptr(on), _lib.ptr(counts),
+                                              self._stream()), "brs_route_triples")
+        send = torch.stack([ou, op_, on], dim=1)  # [n, 3] int64, grouped by destination
+        recv, _ = all_to_all_v(send, counts.cpu().tolist(), self.group)
+        return recv[:, 0].contiguous(), recv[:, 1].contiguous(), recv[:, 2].contiguous()
+
+    def launch_step(self, batch, global_batch=None, out=None):
+        """Enqueue one step (no host sync unless routing is on).  `batch`: this rank's
+        (users, pos, neg) GLOBAL ids.  global_batch defaults to world * len(batch)."""
+        users, pos, neg = (as_index(x, self.device) for x in batch)
+        gb = int(global_batch) if global_batch is not None else users.numel() * self.world
+        if self.route == "owner":
+            users, pos, neg = self.route_triples(users, pos, neg)
+        _lib.check(self.lib.brs_mf_sharded_bpr_fwd_bwd(C.byref(self._cmodel), _lib.ptr(users), _lib.ptr(pos),
+                                                       _lib.ptr(neg), users.numel(), gb, float(self.reg),
+                                                       self._stream()), "brs_mf_sharded_bpr_fwd_bwd")
+        self._barrier(with_sums=True)  # all ranks' peer REDs have landed; step sums exchanged
+        _lib.check(self.lib.brs_mf_apply(C.byref(self._cmodel.local), C.byref(self.opt), gb,
+                                         _lib.ptr(self._out if out is None else out), self._stream()), "brs_mf_apply")
+        self._barrier(with_sums=False)  # every shard updated before anyone gathers again
+
+    def train_single_batch(self, batch, global_batch=None):
+        self.launch_step(batch, global_batch)
+        loss, reg, status, _ = self._out.tolist()
+        if int(status) & 1:
+            raise IndexError("index out of range in self")
+        if status:
+            raise _lib.BrsError("touched-row capacity overflow")
+        return loss, reg
+
+    # -- state --------------------------------------------------------------- #
+    def gather_state(self):
+        """Full state dict in the reference layout (numpy), identical on every rank."""
+        t = self.arena.tensor
+        out = {"global_bias": self.global_bias.cpu().numpy().copy()}
+        for name, key, n in (("user_emb", "user_emb.weight", self.n_users), ("item_emb", "item_emb.weight", self.n_items),
+                             ("user_bias", "user_bias.weight", self.n_users), ("item_bias", "item_bias.weight", self.n_items)):
+            parts = [torch.empty_like(t(name)) for _ in range(self.world)]
+            dist.all_gather(parts, t(name).contiguous(), group=self.group)
+            out[key] = unshard([p.cpu().numpy() for p in parts], n)
+        return out
+
+    def close(self):
+        torch.cuda.synchronize(self.device)
+        self.arena.close()

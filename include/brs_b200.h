@@ -131,7 +131,9 @@ typedef struct brs_mf_model {
 typedef struct brs_mf_peer_tables {
     const float *user_emb, *item_emb, *user_bias, *item_bias;
     float *g_user_emb, *g_item_emb, *g_user_bias, *g_item_bias;
-    const int32_t *user_slot, *item_slot;
+    int32_t *user_slot, *item_slot;    /* slot maps   (brs_rowset.slot_map) */
+    int32_t *user_list, *item_list;    /* slot lists  (brs_rowset.list)     */
+    int32_t *user_count, *item_count;  /* slot counts (brs_rowset.count)    */
 } brs_mf_peer_tables;
 
 /* library / device */
@@ -255,6 +257,56 @@ int brs_dense_adam_sweep(const brs_entity *entities, int32_t n_entities, const b
 /* dense parameters (Linear layers, global bias); clears their grads */
 int brs_dense_params_step(const brs_dense_param *params, int32_t n_params, const brs_opt *opt, int64_t t,
                           void *stream);
+
+/* ---- multi-GPU: row-sharded tables over NVLink peer memory (new work, the
+ *      reference has no distributed path) ----
+ * owner(row) = row mod world, local row = row div world (world a power of two <= 8).  Every rank maps
+ * every other rank's shard (CUDA IPC) and the kernels address it directly: gathers are peer loads,
+ * gradient scatters are peer REDs into the OWNER's compact scratch, slots are claimed with peer atomics.
+ * Ranks meet at two flag barriers per step (no NCCL on the data path). */
+#define BRS_MAX_RANKS 8
+#define BRS_IPC_HANDLE_BYTES 64
+
+/* device memory that can be exported to the other ranks of the node (cudaMalloc'ed, zero-filled) */
+int brs_shm_alloc(int64_t bytes, void **ptr);
+int brs_shm_free(void *ptr);
+int brs_ipc_get_handle(void *ptr, uint8_t handle[BRS_IPC_HANDLE_BYTES]);
+int brs_ipc_open_handle(const uint8_t handle[BRS_IPC_HANDLE_BYTES], void **ptr); /* enables peer access */
+int brs_ipc_close_handle(void *ptr);
+
+typedef struct brs_peer_sync {
+    int32_t world, rank;
+    uint64_t *flags[BRS_MAX_RANKS];   /* flags[r]    = rank r's uint64[BRS_MAX_RANKS] arrival flags (zeroed) */
+    double *partials[BRS_MAX_RANKS];  /* partials[r] = rank r's double[BRS_MAX_RANKS][4] step-sum mailbox   */
+} brs_peer_sync;
+
+/* All ranks call this with the same, strictly increasing `epoch` (1, 2, ...).  Returns (stream-ordered)
+ * once every rank has arrived; writes issued by earlier kernels of every rank (incl. peer REDs) are
+ * visible afterwards.  With ws != NULL the ranks also exchange their step sums {loss, regularizer,
+ * d global_bias}: each rank's ws ends up holding the sums over ALL ranks, added in rank order (so
+ * replicated parameters stay bit-identical). */
+int brs_peer_barrier(const brs_peer_sync *sync, uint64_t epoch, void *ws, void *stream);
+
+typedef struct brs_mf_sharded {
+    int32_t world, rank;
+    int64_t n_users, n_items;            /* GLOBAL row counts */
+    brs_mf_model local;                  /* this rank's shard (tables hold ceil(N/world) rows) */
+    const brs_mf_peer_tables *peers;     /* DEVICE array [world], peers[rank] = own shard */
+} brs_mf_sharded;
+
+/* forward + backward of this rank's `batch` BPR triples (GLOBAL ids) against the sharded tables; the
+ * loss is the mean over `global_batch` = sum of all ranks' batches.  Follow with
+ * brs_peer_barrier(sync, e, local.ws), brs_mf_apply(&local, opt, global_batch, out), brs_peer_barrier(sync, e+1, NULL). */
+int brs_mf_sharded_bpr_fwd_bwd(const brs_mf_sharded *model, const int64_t *users, const int64_t *pos_items,
+                               const int64_t *neg_items, int64_t batch, int64_t global_batch, float reg_weight,
+                               void *stream);
+
+/* stable bucket of (u,i,j) triples by owner(u) = u mod world (the send buffer of the NCCL all-to-all that
+ * routes triples to the user-row owner): out_* hold the triples grouped by destination, original order
+ * kept inside a group; counts[world] (device int64) receives the group sizes */
+int brs_route_triples(const int64_t *users, const int64_t *pos_items, const int64_t *neg_items, int64_t n,
+                      int32_t world, int64_t *out_users, int64_t *out_pos, int64_t *out_neg, int64_t *counts,
+                      void *stream);
 
 /* ---- embedding gather / scatter-add micro-ops (BASELINE.json config 5) ---- */
 int brs_gather(const float *table, int64_t n_rows, int32_t dim, const int64_t *idx, int64_t n, float *out,

@@ -1,0 +1,148 @@
+"""GPU tests of the row-sharded multi-GPU MF path (peer-memory kernels, flag barrier,
+triple routing).  world_size 1 runs on any GPU box; world_size 2/4/8 need that many
+GPUs (skipped otherwise).  Parity target: the sharded engines, each fed its own batch,
+equal the oracle run on the concatenated global batch."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import cf_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _state(rng, nu, ni, d):
+    return {
+        "global_bias": np.array([0.03], dtype=np.float32),
+        "user_emb.weight": rng.normal(0, 0.1, (nu, d)).astype(np.float32),
+        "item_emb.weight": rng.normal(0, 0.1, (ni, d)).astype(np.float32),
+        "user_bias.weight": rng.normal(0, 0.1, (nu, 1)).astype(np.float32),
+        "item_bias.weight": rng.normal(0, 0.1, (ni, 1)).astype(np.float32),
+    }
+
+
+def _zipf(rng, n, size, a=1.05):
+    p = np.arange(1, n + 1, dtype=np.float64) ** (-a)
+    p /= p.sum()
+    return rng.permutation(n)[rng.choice(n, size=size, p=p)].astype(np.int64)
+
+
+def _worker(rank, world, port, route, optimizer, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from beta_recsys_b200.sharded import ShardedMFEngine
+
+        nu, ni, d, bsz, lr, steps = 5003, 1999, 128, 1024, 0.05, 3
+        rng = np.random.default_rng(7)  # same on every rank: the global model and all batches
+        p = _state(rng, nu, ni, d)
+        batches = [[(_zipf(rng, nu, bsz), _zipf(rng, ni, bsz), rng.integers(0, ni, bsz)) for _ in range(world)]
+                   for _ in range(steps)]
+        cfg = {"model": dict(device_str="cuda:%d" % rank, n_users=nu, n_items=ni, emb_dim=d, batch_size=bsz,
+                             optimizer=optimizer, lr=lr, loss="bpr")}
+        eng = ShardedMFEngine(cfg, route=route, state=p)
+        st = O.new_opt_state(p, optimizer)
+        for t in range(steps):
+            loss, reg = eng.train_single_batch(tuple(torch.from_numpy(x).cuda() for x in batches[t][rank]))
+            gu = np.concatenate([b[0] for b in batches[t]])
+            gp = np.concatenate([b[1] for b in batches[t]])
+            gn = np.concatenate([b[2] for b in batches[t]])
+            if optimizer == "sgd" or t == 0:
+                ol, orr = O.mf_train_single_batch(p, st, (gu, gp, gn), "bpr", optimizer, lr, 0.0)
+                assert abs(loss - ol) <= 1e-5 * max(1, abs(ol)), (t, loss, ol)
+                assert abs(reg - orr) <= 1e-5 * max(1, abs(orr)), (t, reg, orr)
+        got = eng.gather_state()
+        if optimizer == "sgd":
+            for k in p:
+                scale = max(np.abs(p[k]).max(), 0.05)
+                err = np.abs(got[k].astype(np.float64) - p[k]).max() / scale
+                assert err <= 1e-5, (k, err)
+        # replicas of the replicated parameter are bit-identical across ranks
+        gb = [torch.empty(1, device="cuda") for _ in range(world)]
+        dist.all_gather(gb, eng.global_bias)
+        assert all(torch.equal(gb[0], x) for x in gb)
+        # scratch is clean again on every rank
+        for name in ("user_slot", "item_slot"):
+            assert bool((eng.arena.tensor(name) == -1).all().item())
+        assert float(eng.arena.tensor("g_user_emb").abs().max().item()) == 0.0
+        eng.close()
+        q.put((rank, "ok"))
+    except Exception as e:  # pragma: no cover
+        import traceback
+
+        q.put((rank, traceback.format_exc()[-1500:]))
+    finally:
+        dist.destroy_process_group()
+
+
+def _run(world, route, optimizer):
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, route, optimizer, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(r, "ok") for r in range(world)], res
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("optimizer", ["sgd", "adam"])
+def test_sharded_world1_matches_oracle(optimizer):
+    _run(1, "none", optimizer)
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("route", ["none", "owner"])
+def test_sharded_world2_matches_oracle_on_the_global_batch(route):
+    _run(2, route, "sgd")
+
+
+@pytest.mark.timeout(300)
+def test_sharded_world2_adam_first_step():
+    _run(2, "none", "adam")
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("world", [4, 8])
+def test_sharded_world_4_8(world):
+    _run(world, "none", "sgd")
+
+
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
+def test_route_triples_kernel_is_bit_exact_vs_oracle(world):
+    from beta_recsys_b200 import _lib
+
+    lib = _lib.load()
+    rng = np.random.default_rng(world)
+    for n in (1, 255, 256, 257, 40000):
+        u, p, ng = rng.integers(0, 10**6, n), rng.integers(0, 10**5, n), rng.integers(0, 10**5, n)
+        tu, tp, tn = (torch.from_numpy(x).cuda() for x in (u, p, ng))
+        ou, op_, on = torch.empty_like(tu), torch.empty_like(tp), torch.empty_like(tn)
+        counts = torch.empty(world, dtype=torch.int64, device="cuda")
+        _lib.check(lib.brs_route_triples(tu.data_ptr(), tp.data_ptr(), tn.data_ptr(), n, world, ou.data_ptr(),
+                                         op_.data_ptr(), on.data_ptr(), counts.data_ptr(),
+                                         torch.cuda.current_stream().cuda_stream))
+        c, ru, rp, rn, _ = O.route_triples(u, p, ng, world)
+        assert np.array_equal(counts.cpu().numpy(), c)
+        assert np.array_equal(ou.cpu().numpy(), ru) and np.array_equal(op_.cpu().numpy(), rp)
+        assert np.array_equal(on.cpu().numpy(), rn)
