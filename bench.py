@@ -52,6 +52,9 @@ def parse():
     ap.add_argument("--profile", action="store_true",
                     help="short run for ncu: no e2e / cpu baseline / clock-load loop (numbers printed are NOT bench values)")
     ap.add_argument("--cpu-steps", type=int, default=0, help="timed CPU steps (0 = auto, ~10-30 s)")
+    ap.add_argument("--route", default="none", choices=["none", "owner"],
+                    help="multi-GPU: 'none' = every rank trains its own triples through peer memory; "
+                         "'owner' = NCCL all-to-all routes triples to the user-row owner first")
     return ap.parse_args()
 
 
@@ -253,6 +256,105 @@ def ncu_traffic():
         return None
 
 
+def run_sharded(a, rank, world, local, dev):
+    """N > 1: tables row-sharded over the ranks (owner = row mod N), per-rank batch fixed (weak scaling).
+    Rows travel over NVLink peer memory inside the fused kernel; two flag barriers per step."""
+    import torch.distributed as dist
+
+    from beta_recsys_b200.sharded import ShardedMFEngine
+
+    cfg = {"model": dict(device_str="cuda:%d" % local, n_users=a.users, n_items=a.items, emb_dim=a.dim,
+                         batch_size=a.batch, optimizer=a.optimizer, lr=0.05, loss="bpr", adam_mode=a.adam_mode)}
+    eng = ShardedMFEngine(cfg, route=a.route)
+    users, pos, neg = make_batches(a.users, a.items, a.batch, N_PREBUILT, SEED + rank, dev)
+    stream = torch.cuda.current_stream(dev)
+    outs = torch.zeros((N_PREBUILT, 4), dtype=torch.float32, device=dev)
+
+    def batch(k):
+        s = slice((k % N_PREBUILT) * a.batch, (k % N_PREBUILT + 1) * a.batch)
+        return users[s], pos[s], neg[s]
+
+    def run_steps(k0, k):
+        for i in range(k0, k0 + k):
+            eng.launch_step(batch(i), out=outs[i % N_PREBUILT])
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    run_steps(0, max(a.warmup, 3))
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.time()
+    e0.record(stream)
+    run_steps(a.warmup, a.steps)
+    e1.record(stream)
+    barrier()
+    t_wall1 = time.time()
+    ms = e0.elapsed_time(e1)
+    assert float(outs[:, 2].max().item()) == 0.0, "kernel reported a non-zero status"
+    final_loss = float(outs[(a.warmup + a.steps - 1) % N_PREBUILT, 0].item())
+    while not a.profile and time.time() - t_wall0 < 1.2:
+        run_steps(0, 64)
+        torch.cuda.synchronize(dev)
+    clocks = sampler.summary(t_wall0, time.time())
+
+    e2e = None
+    if not a.no_e2e:
+        n_e2e = min(a.steps, 200)
+        nb_host = min(N_PREBUILT, n_e2e + 3)
+        hu = users[: nb_host * a.batch].cpu().pin_memory()
+        hp = pos[: nb_host * a.batch].cpu().pin_memory()
+        hn = neg[: nb_host * a.batch].cpu().pin_memory()
+
+        def host_batch(k):
+            s = slice((k % nb_host) * a.batch, (k % nb_host + 1) * a.batch)
+            return hu[s], hp[s], hn[s]
+
+        for k in range(3):
+            eng.train_single_batch(host_batch(k))
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record(stream)
+        for k in range(n_e2e):
+            eng.train_single_batch(host_batch(3 + k))
+        s1.record(stream)
+        barrier()
+        e2e_ms = torch.tensor([s0.elapsed_time(s1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+        e2e = {"value": n_e2e * a.batch * world / (e2e_ms.item() * 1e-3), "unit": "interactions/s",
+               "h2d_bytes_per_step": 3 * 8 * a.batch, "d2h_bytes_per_step": 16, "steps": n_e2e,
+               "api": "ShardedMFEngine.train_single_batch((users,pos,neg)) with pinned host LongTensors, per rank"}
+    sampler.stop()
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = t.item()
+    eng.close()
+    if rank == 0:
+        value = a.steps * a.batch * world / (ms * 1e-3)
+        step_s = ms * 1e-3 / a.steps
+        rows_frac = (world - 1) / world if a.route == "none" else (world - 1) / world * 2.0 / 3.0
+        nvl_bytes = rows_frac * a.batch * (12 * a.dim + 24)  # per direction: row reads in, gradient REDs out
+        line = {
+            "metric": "BPR interactions/sec", "value": value, "unit": "interactions/s", "n_gpus": world,
+            "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": dict(config_dict(a, world), parallelism="row-sharded x%d (owner = row mod N), route=%s" % (world, a.route)),
+            "roofline": {"bound": "nvlink", "kernel": "mf_fwd_bwd_kernel<SHARD> (peer loads + peer REDs)",
+                         "achieved": nvl_bytes / step_s / 1e9, "peak": 770.0, "unit": "GB/s",
+                         "frac": nvl_bytes / step_s / 1e9 / 770.0,
+                         "peak_source": "B200_PROFILING.md measured peer copy, per direction per GPU", "traffic": None,
+                         "note": "bytes that must cross NVLink per rank per step and direction "
+                                 "(remote fraction x batch x 3 rows x 4D, + biases) / whole-step time"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": 5 * a.steps,
+            "final_loss": final_loss, "wall_s_timed_region": t_wall1 - t_wall0,
+        }
+        print(json.dumps(line))
+    dist.destroy_process_group()
+
+
 def run_ours(a):
     from beta_recsys_b200 import _lib
     from beta_recsys_b200.engines import MFEngine
@@ -269,6 +371,7 @@ def run_ours(a):
         import torch.distributed as dist
 
         dist.init_process_group("nccl", device_id=dev)
+        return run_sharded(a, rank, world, local, dev)
     lib = _lib.load()
 
     cfg = {"model": dict(device_str="cuda:%d" % local, n_users=a.users, n_items=a.items, emb_dim=a.dim,

@@ -22,6 +22,8 @@
 // cover whole 128-byte lines.  Persistent grid (resident blocks only), 32-sample
 // tiles double-buffered through TMA, warp-uniform loop control, nothing on the
 // per-sample path waits for an atomic's return value.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 int brs_assign_slots(const brs_rowset* rs, const long long* const* idx, const long long* n, int n_arrays,
@@ -192,7 +194,14 @@ __device__ __forceinline__ void sample_load(const MfArgs& a, const IdxTile& T, i
     if (x.su < 0 || x.si < 0 || x.sj < 0) x.valid = false;  // capacity overflow, flagged by the pre-pass
 }
 
-template <int LPR, int VPL, bool FULL, int LOSS, bool SHARD>
+// FAST = true evaluates the sigmoid / log chain with the MUFU approximations (__expf, __logf,
+// __fdividef): ~1e-6 relative on the scores, used only by experimental variants
+template <bool FAST>
+__device__ __forceinline__ float sig_(float x) {
+    return FAST ? __fdividef(1.0f, 1.0f + __expf(-x)) : sigmoidf_(x);
+}
+
+template <int LPR, int VPL, bool FULL, int LOSS, bool SHARD, bool FAST>
 __device__ __forceinline__ void sample_finish(const MfArgs& a, const Sample<VPL, LOSS>& x, int gl, int D, float bg,
                                               float& loss_acc, float& reg_acc, float& gb_acc) {
     float dp = 0.f, dn = 0.f, uu = 0.f, ii = 0.f, jj = 0.f;
@@ -213,11 +222,18 @@ __device__ __forceinline__ void sample_finish(const MfArgs& a, const Sample<VPL,
     float loss_k;
     if (LOSS == LOSS_BPR) {
         // mf.py:43-48 then torch_engine.py:104-105
-        const float sp = sigmoidf_(dp + x.bu + x.bi + bg);
-        const float sn = sigmoidf_(dn + x.bu + x.bj + bg);
+        const float sp = sig_<FAST>(dp + x.bu + x.bi + bg);
+        const float sn = sig_<FAST>(dn + x.bu + x.bj + bg);
         const float d = sp - sn;
-        loss_k = -logsigmoidf_(d);
-        const float dx = -a.inv_b / (1.0f + expf(d));  // d/dx of -mean(logsigmoid(x))
+        float dx;
+        if (FAST) {
+            const float e = __expf(-fabsf(d));  // one exp serves both logsigmoid(d) and sigmoid(-d)
+            loss_k = -(fminf(d, 0.0f) - __logf(1.0f + e));
+            dx = -a.inv_b * (d >= 0.f ? __fdividef(e, 1.0f + e) : __fdividef(1.0f, 1.0f + e));
+        } else {
+            loss_k = -logsigmoidf_(d);
+            dx = -a.inv_b / (1.0f + expf(d));  // d/dx of -mean(logsigmoid(x))
+        }
         cu_i = dx * sp * (1.0f - sp);
         cu_j = -dx * sn * (1.0f - sn);
     } else {
@@ -308,8 +324,8 @@ __device__ __forceinline__ bool stage_tile(const MfArgs& a, long long t, IdxTile
     return used_tma;
 }
 
-template <int LPR, int VPL, bool FULL, int LOSS, bool SHARD>
-__global__ void __launch_bounds__(kThreads, (VPL <= 2) ? 8 : (SHARD ? 4 : 5)) mf_fwd_bwd_kernel(const MfArgs a) {
+template <int LPR, int VPL, bool FULL, int LOSS, bool SHARD, int UNROLL, int MINB, bool FAST>
+__global__ void __launch_bounds__(kThreads, MINB) mf_fwd_bwd_kernel(const MfArgs a) {
     constexpr int SPW = 32 / LPR;
     __shared__ IdxTile s_tile[2];
     __shared__ __align__(8) uint64_t s_bar[2];
@@ -357,10 +373,16 @@ __global__ void __launch_bounds__(kThreads, (VPL <= 2) ? 8 : (SHARD ? 4 : 5)) mf
         const IdxTile& T = s_tile[buf];
         const int tile_n = (int)min((long long)kTile, a.batch - t * kTile);
 
-        for (int b0 = warp * SPW; b0 < tile_n; b0 += kWarps * SPW) {
-            Sample<VPL, LOSS> x;
-            sample_load<LPR, VPL, FULL, LOSS, SHARD>(a, T, b0 + grp, tile_n, gl, D, x);
-            sample_finish<LPR, VPL, FULL, LOSS, SHARD>(a, x, gl, D, bg, loss_acc, reg_acc, gb_acc);
+        // UNROLL passes (UNROLL * SPW samples) in flight per warp: all their loads are issued
+        // before the first one is consumed, and their scalar chains interleave
+        for (int b0 = warp * SPW; b0 < tile_n; b0 += UNROLL * kWarps * SPW) {
+            Sample<VPL, LOSS> x[UNROLL];
+#pragma unroll
+            for (int q = 0; q < UNROLL; ++q)
+                sample_load<LPR, VPL, FULL, LOSS, SHARD>(a, T, b0 + q * kWarps * SPW + grp, tile_n, gl, D, x[q]);
+#pragma unroll
+            for (int q = 0; q < UNROLL; ++q)
+                sample_finish<LPR, VPL, FULL, LOSS, SHARD, FAST>(a, x[q], gl, D, bg, loss_acc, reg_acc, gb_acc);
         }
         __syncthreads();  // everyone is done with s_tile[buf] before it is refilled
     }
@@ -435,16 +457,44 @@ int grid_for(const void* kernel, long long work_blocks) {
     return (int)(g < 1 ? 1 : g);
 }
 
+// experimental lane mappings for D = 128, picked at run time with BRS_MF_VARIANT (tools/sweep_mf.py)
+int g_mf_variant = -1;
+int mf_variant() {
+    if (g_mf_variant < 0) {
+        const char* e = getenv("BRS_MF_VARIANT");
+        g_mf_variant = e ? atoi(e) : 0;
+    }
+    return g_mf_variant;
+}
+
 template <int LOSS, bool SHARD = false>
 int launch_fwd_bwd(const MfArgs& a, cudaStream_t st) {
     const int D = a.dim;
     const long long n_tiles = (a.batch + kTile - 1) / kTile;
-#define BRS_LAUNCH(LPR, VPL, FULL)                                                      \
+#define BRS_LAUNCHX(LPR, VPL, FULL, UNROLL, MINB, FAST)                                 \
     do {                                                                                \
-        auto k = mf_fwd_bwd_kernel<LPR, VPL, FULL, LOSS, SHARD>;                        \
+        auto k = mf_fwd_bwd_kernel<LPR, VPL, FULL, LOSS, SHARD, UNROLL, MINB, FAST>;    \
         k<<<grid_for((const void*)k, n_tiles), kThreads, 0, st>>>(a);                   \
     } while (0)
+#define BRS_LAUNCH(LPR, VPL, FULL) BRS_LAUNCHX(LPR, VPL, FULL, 1, ((VPL) <= 2 ? 8 : (SHARD ? 4 : 5)), false)
     if (D % 4 != 0 || D <= 0 || D > 512) return BRS_ERR_UNSUPPORTED;
+    if (D == 128 && LOSS == LOSS_BPR && !SHARD && mf_variant() != 0) {
+        switch (mf_variant()) {
+            case 1: BRS_LAUNCHX(8, 4, true, 1, 6, false); break;
+            case 2: BRS_LAUNCHX(16, 2, true, 2, 5, false); break;
+            case 3: BRS_LAUNCHX(16, 2, true, 2, 6, false); break;
+            case 4: BRS_LAUNCHX(32, 1, true, 4, 5, false); break;
+            case 5: BRS_LAUNCHX(8, 4, true, 1, 4, false); break;
+            case 6: BRS_LAUNCHX(8, 4, true, 1, 5, true); break;
+            case 7: BRS_LAUNCHX(8, 4, true, 1, 6, true); break;
+            case 8: BRS_LAUNCHX(16, 2, true, 2, 6, true); break;
+            case 9: BRS_LAUNCHX(4, 8, true, 1, 3, false); break;
+            case 10: BRS_LAUNCHX(8, 4, true, 2, 3, false); break;
+            default: return BRS_ERR_INVALID_ARG;
+        }
+        BRS_CUDA_CHECK(cudaGetLastError());
+        return BRS_OK;
+    }
     switch (D) {  // VPL = 4 float4 per lane wherever D allows: a warp instruction serves 32/LPR samples
         case 4: BRS_LAUNCH(1, 1, true); break;
         case 8: BRS_LAUNCH(1, 2, true); break;
@@ -466,6 +516,7 @@ int launch_fwd_bwd(const MfArgs& a, cudaStream_t st) {
             else BRS_LAUNCH(32, 4, false);
     }
 #undef BRS_LAUNCH
+#undef BRS_LAUNCHX
     BRS_CUDA_CHECK(cudaGetLastError());
     return BRS_OK;
 }
@@ -550,6 +601,11 @@ int brs_mf_fwd_bwd_phases(const brs_mf_model* model, int loss_kind, const int64_
     if (loss_kind == LOSS_BPR) return launch_fwd_bwd<LOSS_BPR>(a, st);
     if (loss_kind == LOSS_BCE) return launch_fwd_bwd<LOSS_BCE>(a, st);
     return BRS_ERR_INVALID_ARG;
+}
+
+extern "C" int brs_debug_set_mf_variant(int variant) {
+    g_mf_variant = variant < 0 ? 0 : variant;
+    return BRS_OK;
 }
 
 extern "C" int brs_mf_bpr_fwd_bwd(const brs_mf_model* model, const int64_t* users, const int64_t* pos_items,

@@ -161,6 +161,10 @@ int brs_mf_bpr_prepare(const brs_mf_model *model, const int64_t *users, const in
 int brs_mf_bpr_fwd_bwd_prepared(const brs_mf_model *model, const int64_t *users, const int64_t *pos_items,
                                 const int64_t *neg_items, int64_t batch, float reg_weight, void *stream);
 
+/* diagnostics: select an experimental lane mapping of the fused MF kernel (0 = production default;
+ * also settable with the BRS_MF_VARIANT environment variable); see tools/sweep_mf.py */
+int brs_debug_set_mf_variant(int variant);
+
 /* Same for loss == "bce" (beta_rec/models/mf.py:108-111; torch_engine.py:108-121, nn.BCELoss). */
 int brs_mf_bce_fwd_bwd(const brs_mf_model *model, const int64_t *users, const int64_t *items,
                        const float *ratings, int64_t batch, float reg_weight, void *stream);
