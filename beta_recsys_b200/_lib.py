@@ -98,6 +98,7 @@ _PROTOTYPES = {
     "brs_mf_bpr_prepare": (C.c_int, [C.POINTER(MfModel), _P, _P, _P, C.c_int64, _P]),
     "brs_mf_bpr_fwd_bwd_prepared": (C.c_int, [C.POINTER(MfModel), _P, _P, _P, C.c_int64, C.c_float, _P]),
     "brs_debug_set_mf_variant": (C.c_int, [C.c_int]),
+    "brs_debug_set_l2_policy": (C.c_int, [C.c_int, C.c_int, C.c_int]),
     "brs_mf_bce_fwd_bwd": (C.c_int, [C.POINTER(MfModel), _P, _P, _P, C.c_int64, C.c_float, _P]),
     "brs_mf_apply": (C.c_int, [C.POINTER(MfModel), C.POINTER(Opt), C.c_int64, _P, _P]),
     "brs_mf_train_batches": (C.c_int, [C.POINTER(MfModel), C.POINTER(Opt), C.c_int32, _P, _P, _P, C.c_int64,

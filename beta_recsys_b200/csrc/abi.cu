@@ -37,6 +37,19 @@ int brs_sm_count() {
     return g_sm_count;
 }
 
+namespace {
+brs_l2_policy_cfg g_l2 = {BRS_L2_NORMAL, BRS_L2_NORMAL, BRS_L2_NORMAL};
+}
+const brs_l2_policy_cfg& brs_l2_cfg() { return g_l2; }
+
+extern "C" int brs_debug_set_l2_policy(int gather, int scratch, int weight) {
+    if (gather < 0 || gather > 2 || scratch < 0 || scratch > 2 || weight < 0 || weight > 2) return BRS_ERR_INVALID_ARG;
+    g_l2.gather = gather;
+    g_l2.scratch = scratch;
+    g_l2.weight = weight;
+    return BRS_OK;
+}
+
 extern "C" int brs_abi_version(void) { return BRS_ABI_VERSION; }
 
 extern "C" const char* brs_strerror(int status) {

@@ -35,6 +35,54 @@ __device__ __forceinline__ float4 ld_row4(const float* p) {
     return r;
 }
 
+// L2 eviction-priority policies (createpolicy + L2::cache_hint).  Round-1 sweep: the fused kernel's
+// time did not react to occupancy / ILP / lane mapping, while ~60% of its RED sectors missed L2 and
+// became random 32-byte DRAM read-modify-writes.  The compact gradient scratch is therefore pinned
+// with evict_last, and streamed weight traffic can be demoted with evict_first.
+enum { BRS_L2_NORMAL = 0, BRS_L2_EVICT_FIRST = 1, BRS_L2_EVICT_LAST = 2 };
+__device__ __forceinline__ unsigned long long l2_policy(int kind) {
+    unsigned long long p;
+    if (kind == BRS_L2_EVICT_FIRST)
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    else if (kind == BRS_L2_EVICT_LAST)
+        asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    else
+        asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ float4 ld_row4_pol(const float* p, unsigned long long pol) {
+    float4 r;
+    asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ float4 ld4_pol(const float* p, unsigned long long pol) {
+    float4 r;
+    asm volatile("ld.global.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p), "l"(pol)
+                 : "memory");
+    return r;
+}
+__device__ __forceinline__ void st4_pol(float* p, float4 v, unsigned long long pol) {
+    asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+                 "f"(v.w), "l"(pol)
+                 : "memory");
+}
+__device__ __forceinline__ void red_add4_pol(float* p, float4 v, unsigned long long pol) {
+    asm volatile("red.relaxed.gpu.global.add.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "f"(v.x),
+                 "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol)
+                 : "memory");
+}
+// process-wide policy selection (diagnostics: brs_debug_set_l2_policy)
+struct brs_l2_policy_cfg {
+    int gather;   // embedding-row gathers in the fused kernels
+    int scratch;  // compact gradient scratch: REDs, reads, zeroing
+    int weight;   // weight-row updates in the apply kernels
+};
+const brs_l2_policy_cfg& brs_l2_cfg();
+
 // Gradient-scratch layout.  For dim % 8 == 0 the compact scratch of a table is stored
 // "sector-blocked": [dim/8][capacity][8 floats], i.e. element (slot, col) lives at
 //     ((col >> 3) * capacity + slot) * 8 + (col & 7).

@@ -86,6 +86,7 @@ struct MfArgs {
     const MfPeerTables* __restrict__ peers;
     int shard_shift, shard_mask;
     int user_cap, item_cap;  // capacity of the gradient scratch (sector-blocked layout, common.cuh gs_off)
+    int pol_gather, pol_scratch;  // L2 eviction policies (BRS_L2_*)
     brs_step_ws* ws;
     const long long* users;
     const long long* items;  // pos items (bpr) / items (bce)
@@ -124,7 +125,7 @@ struct Sample {
 
 template <int LPR, int VPL, bool FULL, int LOSS, bool SHARD>
 __device__ __forceinline__ void sample_load(const MfArgs& a, const IdxTile& T, int s, int tile_n, int gl, int D,
-                                            Sample<VPL, LOSS>& x) {
+                                            unsigned long long pol_g, Sample<VPL, LOSS>& x) {
     x.valid = s < tile_n;
     const int sc = x.valid ? s : 0;
     x.u = T.a[sc];
@@ -173,9 +174,9 @@ __device__ __forceinline__ void sample_load(const MfArgs& a, const IdxTile& T, i
     for (int v = 0; v < VPL; ++v) {
         const int col = (v * LPR + gl) * 4;
         const bool on = FULL || col < D;
-        x.ue[v] = on ? ld_row4(ur + col) : f4_zero();
-        x.ie[v] = on ? ld_row4(ir + col) : f4_zero();
-        if (LOSS == LOSS_BPR) x.je[v] = on ? ld_row4(jr + col) : f4_zero();
+        x.ue[v] = on ? ld_row4_pol(ur + col, pol_g) : f4_zero();
+        x.ie[v] = on ? ld_row4_pol(ir + col, pol_g) : f4_zero();
+        if (LOSS == LOSS_BPR) x.je[v] = on ? ld_row4_pol(jr + col, pol_g) : f4_zero();
     }
     x.bu = __ldg(t_ub + lu);
     x.bi = __ldg(t_ib + li);
@@ -203,7 +204,8 @@ __device__ __forceinline__ float sig_(float x) {
 
 template <int LPR, int VPL, bool FULL, int LOSS, bool SHARD, bool FAST>
 __device__ __forceinline__ void sample_finish(const MfArgs& a, const Sample<VPL, LOSS>& x, int gl, int D, float bg,
-                                              float& loss_acc, float& reg_acc, float& gb_acc) {
+                                              unsigned long long pol_s, float& loss_acc, float& reg_acc,
+                                              float& gb_acc) {
     float dp = 0.f, dn = 0.f, uu = 0.f, ii = 0.f, jj = 0.f;
 #pragma unroll
     for (int v = 0; v < VPL; ++v) {
@@ -275,14 +277,14 @@ __device__ __forceinline__ void sample_finish(const MfArgs& a, const Sample<VPL,
             float4 du = f4_scale(cu_i, x.ie[v]);
             if (LOSS == LOSS_BPR) du = f4_fma(cu_j, x.je[v], du);
             if (a.reg_w != 0.f) du = f4_fma(fwd_calls * rw, x.ue[v], du);
-            red_add4(gu + gs_off(D, a.user_cap, (unsigned)x.su, col), du);
+            red_add4_pol(gu + gs_off(D, a.user_cap, (unsigned)x.su, col), du, pol_s);
             float4 di = f4_scale(cu_i, x.ue[v]);
             if (a.reg_w != 0.f) di = f4_fma(rw, x.ie[v], di);
-            red_add4(gi + gs_off(D, a.item_cap, (unsigned)x.si, col), di);
+            red_add4_pol(gi + gs_off(D, a.item_cap, (unsigned)x.si, col), di, pol_s);
             if (LOSS == LOSS_BPR) {
                 float4 dj = f4_scale(cu_j, x.ue[v]);
                 if (a.reg_w != 0.f) dj = f4_fma(rw, x.je[v], dj);
-                red_add4(gj + gs_off(D, a.item_cap, (unsigned)x.sj, col), dj);
+                red_add4_pol(gj + gs_off(D, a.item_cap, (unsigned)x.sj, col), dj, pol_s);
             }
         }
     }
@@ -348,6 +350,7 @@ __global__ void __launch_bounds__(kThreads, MINB) mf_fwd_bwd_kernel(const MfArgs
     __syncthreads();
 
     const float bg = __ldg(a.global_bias);
+    const unsigned long long pol_g = l2_policy(a.pol_gather), pol_s = l2_policy(a.pol_scratch);
     float loss_acc = 0.f, reg_acc = 0.f, gb_acc = 0.f;
     unsigned phase_bits = 0u;  // bit b = parity to wait for on s_bar[b]
     unsigned tma_bits = 0u;    // bit b = s_tile[b] is being filled by TMA
@@ -379,10 +382,10 @@ __global__ void __launch_bounds__(kThreads, MINB) mf_fwd_bwd_kernel(const MfArgs
             Sample<VPL, LOSS> x[UNROLL];
 #pragma unroll
             for (int q = 0; q < UNROLL; ++q)
-                sample_load<LPR, VPL, FULL, LOSS, SHARD>(a, T, b0 + q * kWarps * SPW + grp, tile_n, gl, D, x[q]);
+                sample_load<LPR, VPL, FULL, LOSS, SHARD>(a, T, b0 + q * kWarps * SPW + grp, tile_n, gl, D, pol_g, x[q]);
 #pragma unroll
             for (int q = 0; q < UNROLL; ++q)
-                sample_finish<LPR, VPL, FULL, LOSS, SHARD, FAST>(a, x[q], gl, D, bg, loss_acc, reg_acc, gb_acc);
+                sample_finish<LPR, VPL, FULL, LOSS, SHARD, FAST>(a, x[q], gl, D, bg, pol_s, loss_acc, reg_acc, gb_acc);
         }
         __syncthreads();  // everyone is done with s_tile[buf] before it is refilled
     }
@@ -558,6 +561,8 @@ int fill_args(const brs_mf_model* m, MfArgs& a, bool need_grad) {
     a.item_cap = m->item.rows.capacity;
     a.peers = nullptr;
     a.shard_shift = a.shard_mask = 0;
+    a.pol_gather = brs_l2_cfg().gather;
+    a.pol_scratch = brs_l2_cfg().scratch;
     a.ws = (brs_step_ws*)m->ws;
     a.n_users = m->user.table[0].n_rows;
     a.n_items = m->item.table[0].n_rows;

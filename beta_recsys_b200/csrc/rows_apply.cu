@@ -162,6 +162,7 @@ struct ApplyArgs {
     float* out;         // device brs_step_out (float[4]) or NULL
     double inv_batch;
     int advance_step;   // last block: ws->step += 1, reset sums
+    int pol_scratch, pol_weight;  // L2 eviction policies (BRS_L2_*)
 };
 
 // one touched row of one table: scratch row `slot` -> weight row `row`
@@ -206,7 +207,8 @@ __device__ __forceinline__ void update_row(const brs_table& tb, int cap, long lo
 // SGD needs no weight load at all: w += -lr*g leaves as a fire-and-forget 128-bit RED.
 template <int KIND, int ROWS>
 __device__ __forceinline__ void update_rows_small(const brs_table& tb, int cap, const int (&row)[ROWS], int s0, int n,
-                                                  int lane, const OptScalars& s) {
+                                                  int lane, const OptScalars& s, unsigned long long pol_s,
+                                                  unsigned long long pol_w) {
     const int d = tb.dim, c = lane * 4;
     if (c >= d) return;
     float4 gv[ROWS], wv[ROWS], mv[ROWS], vv[ROWS];
@@ -215,8 +217,8 @@ __device__ __forceinline__ void update_rows_small(const brs_table& tb, int cap, 
         wv[r] = mv[r] = vv[r] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (r < n) {
             const size_t ro = (size_t)(unsigned)row[r] * (unsigned)d + c;
-            gv[r] = *(const float4*)(tb.grad + gs_off(d, cap, (unsigned)(s0 + r), c));
-            if (KIND != BRS_SGD) wv[r] = *(const float4*)(tb.weight + ro);
+            gv[r] = ld4_pol(tb.grad + gs_off(d, cap, (unsigned)(s0 + r), c), pol_s);
+            if (KIND != BRS_SGD) wv[r] = ld4_pol(tb.weight + ro, pol_w);
             if (KIND == BRS_ADAM) mv[r] = *(const float4*)(tb.m + ro);
             if (KIND != BRS_SGD) vv[r] = *(const float4*)(tb.v + ro);
         }
@@ -226,14 +228,14 @@ __device__ __forceinline__ void update_rows_small(const brs_table& tb, int cap, 
         if (r < n) {
             const size_t ro = (size_t)(unsigned)row[r] * (unsigned)d + c;
             if (KIND == BRS_SGD) {
-                red_add4(tb.weight + ro, make_float4(-s.lr * gv[r].x, -s.lr * gv[r].y, -s.lr * gv[r].z, -s.lr * gv[r].w));
+                red_add4_pol(tb.weight + ro, make_float4(-s.lr * gv[r].x, -s.lr * gv[r].y, -s.lr * gv[r].z, -s.lr * gv[r].w), pol_w);
             } else {
                 opt_elem4<KIND>(wv[r], gv[r], mv[r], vv[r], s);
-                *(float4*)(tb.weight + ro) = wv[r];
+                st4_pol(tb.weight + ro, wv[r], pol_w);
                 if (KIND == BRS_ADAM) *(float4*)(tb.m + ro) = mv[r];
                 *(float4*)(tb.v + ro) = vv[r];
             }
-            *(float4*)(tb.grad + gs_off(d, cap, (unsigned)(s0 + r), c)) = make_float4(0.f, 0.f, 0.f, 0.f);
+            st4_pol(tb.grad + gs_off(d, cap, (unsigned)(s0 + r), c), make_float4(0.f, 0.f, 0.f, 0.f), pol_s);
         }
     }
 }
@@ -332,6 +334,7 @@ __global__ void __launch_bounds__(kThreads) rows_apply_kernel(const ApplyArgs a)
     }
     __syncthreads();
     const OptScalars s = s_opt;
+    const unsigned long long pol_s = l2_policy(a.pol_scratch), pol_w = l2_policy(a.pol_weight);
     const int lane = threadIdx.x & 31;
     const int warp = __shfl_sync(BRS_FULL_MASK, threadIdx.x >> 5, 0);
     const int total = s_cnt[a.n_ent];
@@ -349,7 +352,7 @@ __global__ void __launch_bounds__(kThreads) rows_apply_kernel(const ApplyArgs a)
         for (int k = 0; k < en.n_tables; ++k) {
             const brs_table& tb = en.table[k];
             if ((tb.dim & 3) == 0 && tb.dim <= 128) {
-                update_rows_small<KIND, ROWS>(tb, en.rows.capacity, row, s0, n, lane, s);
+                update_rows_small<KIND, ROWS>(tb, en.rows.capacity, row, s0, n, lane, s, pol_s, pol_w);
             } else if (tb.dim == 1) {  // bias tables: lane q handles row q
                 if (lane < n) update_row<KIND>(tb, en.rows.capacity, my_row, s0 + lane, 0, s);
             } else {
@@ -611,6 +614,8 @@ int brs_apply_impl(const brs_entity* ents, int n_ent, const brs_dense_param* den
     a.out = out;
     a.inv_batch = batch > 0 ? 1.0 / (double)batch : 0.0;
     a.advance_step = ws ? 1 : 0;
+    a.pol_scratch = brs_l2_cfg().scratch;
+    a.pol_weight = brs_l2_cfg().weight;
     cudaStream_t st = (cudaStream_t)stream;
     switch (opt->kind) {
         case BRS_SGD: return launch_apply<BRS_SGD>(a, BRS_TOUCHED_ROWS, max_rows_hint, st);

@@ -164,6 +164,9 @@ int brs_mf_bpr_fwd_bwd_prepared(const brs_mf_model *model, const int64_t *users,
 /* diagnostics: select an experimental lane mapping of the fused MF kernel (0 = production default;
  * also settable with the BRS_MF_VARIANT environment variable); see tools/sweep_mf.py */
 int brs_debug_set_mf_variant(int variant);
+/* diagnostics: L2 eviction priority (0 normal, 1 evict_first, 2 evict_last) used for the embedding-row
+ * gathers, the compact gradient scratch, and the weight-row updates of the apply kernels */
+int brs_debug_set_l2_policy(int gather, int scratch, int weight);
 
 /* Same for loss == "bce" (beta_rec/models/mf.py:108-111; torch_engine.py:108-121, nn.BCELoss). */
 int brs_mf_bce_fwd_bwd(const brs_mf_model *model, const int64_t *users, const int64_t *items,

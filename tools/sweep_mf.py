@@ -25,10 +25,11 @@ def ids(n, size, a, gen, dev):
     return perm[torch.searchsorted(cdf, torch.rand(size, generator=gen, device=dev)).clamp_(max=n - 1)]
 
 
-def run(nu, ni, d, b, a, nb=32, reps=40, sort_users=False, variant=0):
+def run(nu, ni, d, b, a, nb=32, reps=40, sort_users=False, variant=0, pol=(0, 0, 0)):
     dev = torch.device("cuda", 0)
     lib = _lib.load()
     lib.brs_debug_set_mf_variant(variant)
+    lib.brs_debug_set_l2_policy(*pol)
     cfg = {"model": dict(device_str="cuda:0", n_users=nu, n_items=ni, emb_dim=d, batch_size=b, optimizer="sgd",
                          lr=0.05, loss="bpr"), "system": {"run_dir": "/tmp/x"}}
     with redirect_stdout(io.StringIO()):
@@ -58,8 +59,8 @@ def run(nu, ni, d, b, a, nb=32, reps=40, sort_users=False, variant=0):
     torch.cuda.synchronize()
     t = [float(np.median([e[i].elapsed_time(e[i + 1]) for e in ev])) * 1e3 for i in range(3)]
     alg = (24 * d + 48) * b
-    print("var=%2d U=%8d I=%7d D=%3d B=%6d zipf=%.2f sortu=%d | uniq u/i %6d/%6d | prep %6.1f fwd %6.1f apply %6.1f us | "
-          "fwd %.0f GB/s  step %.0f M inter/s" % (variant, nu, ni, d, b, a, sort_users, uniq[0], uniq[1], t[0], t[1], t[2],
+    print("pol=%s var=%2d U=%8d I=%7d D=%3d B=%6d zipf=%.2f sortu=%d | uniq u/i %6d/%6d | prep %6.1f fwd %6.1f apply %6.1f us | "
+          "fwd %.0f GB/s  step %.0f M inter/s" % ("".join(map(str, pol)), variant, nu, ni, d, b, a, sort_users, uniq[0], uniq[1], t[0], t[1], t[2],
                                                    alg / t[1] / 1e3, b / sum(t)), flush=True)
     del eng
     torch.cuda.empty_cache()
@@ -67,6 +68,15 @@ def run(nu, ni, d, b, a, nb=32, reps=40, sort_users=False, variant=0):
 
 if __name__ == "__main__":
     B = 65536
+    if len(sys.argv) > 1 and sys.argv[1] == "l2":
+        for pol in ((0, 0, 0), (0, 2, 0), (1, 2, 0), (1, 2, 1), (0, 2, 1), (1, 0, 0), (1, 2, 2), (2, 2, 0)):
+            run(1_000_000, 100_000, 128, B, 1.05, pol=pol)
+        for pol in ((0, 0, 0), (1, 2, 1)):
+            run(1_000_000, 100_000, 128, B, 0.0, pol=pol)
+            run(4_000_000, 1_000_000, 128, B, 1.05, pol=pol)
+            run(1_000_000, 100_000, 64, B, 1.05, pol=pol)
+            run(1_000_000, 100_000, 256, B, 1.05, pol=pol)
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "variants":
         for v in range(0, 11):
             run(1_000_000, 100_000, 128, B, 1.05, variant=v)
