@@ -63,6 +63,21 @@ class NcfModel(C.Structure):
                 ("mfv", C.c_void_p), ("dz", C.c_void_p), ("max_batch", C.c_int64), ("ws", C.c_void_p)]
 
 
+LGCN_MAX_LAYERS = 6
+
+
+class Csr(C.Structure):
+    _fields_ = [("row_ptr", C.c_void_p), ("col", C.c_void_p), ("val", C.c_void_p), ("edge_id", C.c_void_p),
+                ("n_rows", C.c_int64), ("nnz", C.c_int64)]
+
+
+class LightGCNModel(C.Structure):
+    _fields_ = [("n_users", C.c_int64), ("n_items", C.c_int64), ("dim", C.c_int32), ("n_layers", C.c_int32),
+                ("decay", C.c_float), ("pad_", C.c_float), ("adj", Csr), ("adj_t", Csr),
+                ("emb", C.c_void_p * (LGCN_MAX_LAYERS + 1)), ("d", C.c_void_p), ("g", C.c_void_p * 2),
+                ("param", DenseParam), ("ws", C.c_void_p)]
+
+
 MAX_RANKS = 8
 IPC_HANDLE_BYTES = 64
 
@@ -83,7 +98,7 @@ class MfSharded(C.Structure):
                 ("local", MfModel), ("peers", C.c_void_p)]
 
 
-EXTRA_STRUCTS = {"brs_ncf_model": NcfModel, "brs_mf_peer_tables": MfPeerTables, "brs_peer_sync": PeerSync,
+EXTRA_STRUCTS = {"brs_csr": Csr, "brs_lightgcn_model": LightGCNModel, "brs_ncf_model": NcfModel, "brs_mf_peer_tables": MfPeerTables, "brs_peer_sync": PeerSync,
                  "brs_mf_sharded": MfSharded}
 
 _P = C.c_void_p
@@ -111,6 +126,11 @@ _PROTOTYPES = {
                                         _P]),
     "brs_mlp_fwd": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _P]),
     "brs_mlp_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int32, C.c_int32, _P]),
+    "brs_spmm_csr": (C.c_int, [C.POINTER(Csr), _P, C.c_float, _P, _P, C.c_int32, _P]),
+    "brs_lightgcn_propagate": (C.c_int, [C.POINTER(LightGCNModel), _P, C.c_float, _P]),
+    "brs_lightgcn_fwd_bwd": (C.c_int, [C.POINTER(LightGCNModel), _P, C.c_float, _P, _P, _P, C.c_int64, _P]),
+    "brs_lightgcn_apply": (C.c_int, [C.POINTER(LightGCNModel), C.POINTER(Opt), C.c_int64, _P, _P]),
+    "brs_lightgcn_scores": (C.c_int, [C.POINTER(LightGCNModel), _P, _P, C.c_int64, _P, _P]),
     "brs_rows_assign": (C.c_int, [C.POINTER(Rowset), _P, C.c_int64, _P, _P]),
     "brs_rows_scatter_grad": (C.c_int, [C.POINTER(Entity), C.c_int32, _P, C.c_int64, _P, C.c_float, _P]),
     "brs_rows_sgd": (C.c_int, [C.POINTER(Entity), C.c_int32, C.c_double, _P]),

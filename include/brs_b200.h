@@ -247,6 +247,55 @@ int brs_mlp_fwd(const float *x, const float *w, const float *b, float *y, int64_
 int brs_mlp_bwd(const float *dy, const float *x, const float *w, float *dx, float *dw, float *db,
                 const float *relu_mask_src, int64_t m, int32_t n, int32_t k, void *stream);
 
+/* ---- LightGCN: beta_rec/models/lightgcn.py ---- */
+#define BRS_LGCN_MAX_LAYERS 6
+
+/* CSR sparse matrix; nnz < 2^31.  edge_id (optional) maps each stored non-zero back to its position in the
+ * coalesced (row-major) edge list of the ORIGINAL matrix -- used by the transpose so that it consumes the
+ * same edge-dropout keep mask as the forward matrix */
+typedef struct brs_csr {
+    const int32_t *row_ptr;  /* [n_rows + 1] */
+    const int32_t *col;      /* [nnz] */
+    const float *val;        /* [nnz] */
+    const int32_t *edge_id;  /* [nnz] or NULL (identity) */
+    int64_t n_rows, nnz;
+} brs_csr;
+
+/* y[r, :] += sum over kept non-zeros e of row r of (val[e] / keep_prob) * x[col[e], :]
+ * (torch.sparse.mm at lightgcn.py:73 with LightGCN.dropout's mask/rescale at :32-36 folded in).
+ * keep_mask: uint8 per ORIGINAL edge, or NULL for no dropout.  y must be pre-initialised. */
+int brs_spmm_csr(const brs_csr *a, const uint8_t *keep_mask, float keep_prob, const float *x, float *y, int32_t dim,
+                 void *stream);
+
+typedef struct brs_lightgcn_model {
+    int64_t n_users, n_items;
+    int32_t dim, n_layers;
+    float decay;  /* regs[0] (lightgcn.py:113) */
+    float pad_;
+    brs_csr adj;    /* norm_adj = D^-1 (A + I), [N, N], N = n_users + n_items (row-normalised => asymmetric) */
+    brs_csr adj_t;  /* its transpose in CSR, edge_id -> edge of adj */
+    float *emb[BRS_LGCN_MAX_LAYERS + 1]; /* emb[0] = the parameters [N, dim] (users first, then items:
+                                            torch.cat at lightgcn.py:55-57); emb[l] = layer-l buffer */
+    float *d;         /* [N, dim] scratch: d loss / d E^(l) */
+    float *g[2];      /* [N, dim] x2 scratch for the backward chain */
+    brs_dense_param param;  /* weight = emb[0]; grad [N, dim] receives d loss / d E^(0); m, v for Adam */
+    void *ws;
+} brs_lightgcn_model;
+
+/* LightGCN.forward's propagate (lightgcn.py:46-74): fills emb[1..L] */
+int brs_lightgcn_propagate(const brs_lightgcn_model *model, const uint8_t *keep_mask, float keep_prob, void *stream);
+/* train_single_batch minus the optimizer (lightgcn.py:119-149): propagate, softplus-BPR + L2 tail, backward
+ * through the propagate; the dense gradient of the embeddings lands in param.grad */
+int brs_lightgcn_fwd_bwd(const brs_lightgcn_model *model, const uint8_t *keep_mask, float keep_prob,
+                         const int64_t *users, const int64_t *pos_items, const int64_t *neg_items, int64_t batch,
+                         void *stream);
+/* optimizer.step() over all rows + loss.item() (lightgcn.py:150-151) */
+int brs_lightgcn_apply(const brs_lightgcn_model *model, const brs_opt *opt, int64_t batch,
+                       float *out /* brs_step_out */, void *stream);
+/* sigmoid(ebar_u . ebar_i) from the current layer buffers (LightGCN.predict, lightgcn.py:80-101) */
+int brs_lightgcn_scores(const brs_lightgcn_model *model, const int64_t *users, const int64_t *items, int64_t n,
+                        float *scores, void *stream);
+
 /* ---- generic sparse-embedding-gradient building blocks (K5/K6 in SURVEY.md section 2b) ---- */
 /* range-check idx[0..n) against rows->n_rows and give every distinct row a slot in the entity's
  * compact gradient scratch (ws: BRS_STEP_WS_BYTES of zeroed device scratch; ws.err_flag collects errors) */
