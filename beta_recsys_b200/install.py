@@ -17,6 +17,8 @@ _BINDINGS = [
     ("beta_rec.models.ncf", "NeuMFEngine", "NeuMFEngine"),
     ("beta_rec.models.gmf", "GMFEngine", "GMFEngine"),
     ("beta_rec.models.mlp", "MLPEngine", "MLPEngine"),
+    ("beta_rec.recommenders.lightgcn", "LightGCNEngine", "LightGCNEngine"),
+    ("beta_rec.models.lightgcn", "LightGCNEngine", "LightGCNEngine"),
 ]
 _saved = {}
 
