@@ -58,7 +58,7 @@ class NcfModel(C.Structure):
     _fields_ = [("kind", C.c_int32), ("n_layers", C.c_int32), ("emb_dim", C.c_int32), ("mlp_dim", C.c_int32),
                 ("user", Entity), ("item", Entity),
                 ("fc_weight", DenseParam * NCF_MAX_LAYERS), ("fc_bias", DenseParam * NCF_MAX_LAYERS),
-                ("out_weight", DenseParam), ("out_bias", DenseParam),
+                ("fc_weight_t", C.c_void_p * NCF_MAX_LAYERS), ("out_weight", DenseParam), ("out_bias", DenseParam),
                 ("act", C.c_void_p * (NCF_MAX_LAYERS + 1)), ("dact", C.c_void_p * (NCF_MAX_LAYERS + 1)),
                 ("mfv", C.c_void_p), ("dz", C.c_void_p), ("max_batch", C.c_int64), ("ws", C.c_void_p)]
 
@@ -124,6 +124,8 @@ _PROTOTYPES = {
     "brs_ncf_predict": (C.c_int, [C.POINTER(NcfModel), _P, _P, C.c_int64, _P, _P]),
     "brs_ncf_train_batches": (C.c_int, [C.POINTER(NcfModel), C.POINTER(Opt), _P, _P, _P, C.c_int64, C.c_int64, _P,
                                         _P]),
+    "brs_mlp_fwd_tc": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _P]),
+    "brs_set_gemm_backend": (C.c_int, [C.c_int]),
     "brs_mlp_fwd": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _P]),
     "brs_mlp_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int32, C.c_int32, _P]),
     "brs_spmm_csr": (C.c_int, [C.POINTER(Csr), _P, C.c_float, _P, _P, C.c_int32, _P]),

@@ -23,6 +23,10 @@ int brs_linear_dgrad_simt(const float* dY, int ldy, const float* W, float* dX, i
                           int M, int N, int K, cudaStream_t st);
 int brs_linear_wgrad_simt(const float* dY, int ldy, const float* X, int ldx, float* dW, float* db, int M, int N, int K,
                           cudaStream_t st);
+bool brs_linear_tc_supported(int M, int N, int K);
+int brs_linear_tc(const float* A, const float* B, const float* bias, float* Y, const float* mask, int M, int N, int K,
+                  bool relu, cudaStream_t st);
+int brs_transpose(const float* src, float* dst, int R, int C, cudaStream_t st);
 int brs_assign_slots(const brs_rowset* rs, const long long* const* idx, const long long* n, int n_arrays,
                      brs_step_ws* ws, cudaStream_t st);
 int brs_apply_impl(const brs_entity* ents, int n_ent, const brs_dense_param* dense, int n_dense,
@@ -33,6 +37,9 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
+
+// 0 = exact-fp32 FFMA kernels (gemm_simt.cu), 1 = tcgen05 3xTF32 (gemm_tc.cu) where the shape allows
+int g_gemm_backend = 1;
 
 struct NcfArgs {
     int kind;      // BRS_NCF_GMF / MLP / NEUMF
@@ -406,7 +413,12 @@ int forward(const brs_ncf_model* m, const NcfArgs& a, cudaStream_t st) {
     BRS_CUDA_CHECK(cudaGetLastError());
     for (int l = 0; l < m->n_layers; ++l) {
         const int in = layer_in(m, l), out = in / 2;
-        int rc = brs_linear_fwd_simt(m->act[l], in, m->fc_weight[l].weight, m->fc_bias[l].weight, m->act[l + 1], out,
+        int rc;
+        if (g_gemm_backend == 1 && brs_linear_tc_supported((int)a.batch, out, in))
+            rc = brs_linear_tc(m->act[l], m->fc_weight[l].weight, m->fc_bias[l].weight, m->act[l + 1], nullptr,
+                               (int)a.batch, out, in, /*relu=*/true, st);
+        else
+            rc = brs_linear_fwd_simt(m->act[l], in, m->fc_weight[l].weight, m->fc_bias[l].weight, m->act[l + 1], out,
                                      (int)a.batch, out, in, /*relu=*/true, st);
         if (rc != BRS_OK) return rc;
     }
@@ -448,8 +460,16 @@ extern "C" int brs_ncf_fwd_bwd(const brs_ncf_model* model, const int64_t* users,
         if (rc != BRS_OK) return rc;
         // mask by (layer input > 0): a ReLU precedes every Linear except MLP's first (mlp.py:47-48)
         const float* mask = (l == 0 && model->kind == BRS_NCF_MLP) ? nullptr : model->act[l];
-        rc = brs_linear_dgrad_simt(model->dact[l + 1], out, model->fc_weight[l].weight, model->dact[l], in, mask, in,
-                                   (int)batch, out, in, st);
+        if (g_gemm_backend == 1 && model->fc_weight_t[l] && brs_linear_tc_supported((int)batch, in, out)) {
+            // dX[M,in] = dY[M,out] . W[out,in]  ==  dY . (W^T)^T with W^T [in,out] as the K-major B operand
+            rc = brs_transpose(model->fc_weight[l].weight, model->fc_weight_t[l], out, in, st);
+            if (rc != BRS_OK) return rc;
+            rc = brs_linear_tc(model->dact[l + 1], model->fc_weight_t[l], nullptr, model->dact[l], mask, (int)batch, in,
+                               out, /*relu=*/false, st);
+        } else {
+            rc = brs_linear_dgrad_simt(model->dact[l + 1], out, model->fc_weight[l].weight, model->dact[l], in, mask, in,
+                                       (int)batch, out, in, st);
+        }
         if (rc != BRS_OK) return rc;
     }
     ncf_scatter_kernel<<<grid_warp_per_sample(batch, (const void*)ncf_scatter_kernel), kThreads, 0, st>>>(a);
@@ -510,6 +530,20 @@ extern "C" int brs_ncf_train_batches(const brs_ncf_model* model, const brs_opt* 
 }
 
 // the Linear building blocks, exposed for tests / other callers (brs_mlp_{fwd,bwd})
+extern "C" int brs_set_gemm_backend(int backend) {
+    if (backend != 0 && backend != 1) return BRS_ERR_INVALID_ARG;
+    g_gemm_backend = backend;
+    return BRS_OK;
+}
+
+// tensor-core Linear building block: y = epilogue(x[m,k] . w[n,k]^T) with 3xTF32 error compensation
+extern "C" int brs_mlp_fwd_tc(const float* x, const float* w, const float* b, float* y, const float* keep_where_positive,
+                              int64_t m, int32_t n, int32_t k, int32_t relu, void* stream) {
+    if (!x || !w || !y || m < 0 || n <= 0 || k <= 0) return BRS_ERR_INVALID_ARG;
+    if (m == 0) return BRS_OK;
+    return brs_linear_tc(x, w, b, y, keep_where_positive, (int)m, n, k, relu != 0, (cudaStream_t)stream);
+}
+
 extern "C" int brs_mlp_fwd(const float* x, const float* w, const float* b, float* y, int64_t m, int32_t n, int32_t k,
                            int32_t relu, void* stream) {
     if (!x || !w || !b || !y || m < 0 || n <= 0 || k <= 0) return BRS_ERR_INVALID_ARG;

@@ -185,9 +185,13 @@ class _NcfEngine(ModelEngine):
             for l in range(n_layers + 1):
                 c.act[l] = buf(width >> l)
                 c.dact[l] = buf(width >> l)
+            self._wt = []
             for l, base in enumerate(self._fc_names):
                 c.fc_weight[l] = dense[base + ".weight"]
                 c.fc_bias[l] = dense[base + ".bias"]
+                wt = torch.zeros(((width >> l), (width >> l) // 2), dtype=torch.float32, device=dev)
+                self._wt.append(wt)  # W^T scratch for the tensor-core dgrad
+                c.fc_weight_t[l] = _lib.ptr(wt)
             if self.KIND == _lib.NCF_NEUMF:
                 c.mfv = buf(emb)
         c.out_weight = dense["affine_output.weight"]

@@ -211,6 +211,7 @@ typedef struct brs_ncf_model {
     brs_entity item;   /* same for items */
     brs_dense_param fc_weight[BRS_NCF_MAX_LAYERS]; /* fc_layers.{3l+1}.weight [in_l/2, in_l], in_l = 2*mlp_dim >> l */
     brs_dense_param fc_bias[BRS_NCF_MAX_LAYERS];
+    float *fc_weight_t[BRS_NCF_MAX_LAYERS];        /* scratch [in_l, in_l/2] for W^T (dgrad on tensor cores) or NULL */
     brs_dense_param out_weight;                    /* affine_output.weight [1, emb_dim (GMF, MLP) | 2*emb_dim (NeuMF)] */
     brs_dense_param out_bias;                      /* affine_output.bias [1] */
     float *act[BRS_NCF_MAX_LAYERS + 1];   /* act[0] = tower input [max_batch, 2*mlp_dim], act[l] = output of layer l */
@@ -242,6 +243,13 @@ int brs_ncf_train_batches(const brs_ncf_model *model, const brs_opt *opt, const 
  *   fwd: y[m,n] = (relu)(x[m,k] . w[n,k]^T + b[n])
  *   bwd: dw[n,k] += dy^T x ; db[n] += colsum(dy) (db may be NULL);
  *        dx[m,k] = (dy . w) * (relu_mask_src[m,k] > 0)   (dx may be NULL; mask source may be NULL) */
+/* same forward on the 5th-gen tensor cores: tcgen05.mma kind::tf32 with 3xTF32 error compensation
+ * (hi.hi + hi.lo + lo.hi accumulated in TMEM), fused bias / ReLU / keep-where-positive mask.
+ * Shapes: k % 32 == 0, n % 64 == 0; BRS_ERR_UNSUPPORTED otherwise (callers fall back to brs_mlp_fwd). */
+int brs_mlp_fwd_tc(const float *x, const float *w, const float *b, float *y, const float *keep_where_positive,
+                   int64_t m, int32_t n, int32_t k, int32_t relu, void *stream);
+/* 0 = exact-fp32 FFMA Linear kernels, 1 = tcgen05 3xTF32 where the shape allows (default) */
+int brs_set_gemm_backend(int backend);
 int brs_mlp_fwd(const float *x, const float *w, const float *b, float *y, int64_t m, int32_t n, int32_t k,
                 int32_t relu, void *stream);
 int brs_mlp_bwd(const float *dy, const float *x, const float *w, float *dx, float *dw, float *db,

@@ -249,3 +249,53 @@ def test_linear_building_blocks_vs_numpy(m, n, k):
     assert max_rel_err(tdx.cpu().numpy(), want_dx) <= 2e-6
     assert max_rel_err(tdw.cpu().numpy(), dy.T.astype(np.float64) @ x.astype(np.float64)) <= 4e-6
     assert max_rel_err(tdb.cpu().numpy(), dy.sum(0, dtype=np.float64)) <= 4e-6
+
+
+@pytest.mark.parametrize("m,n,k,relu,use_mask", [(128, 64, 32, 1, 0), (1000, 256, 512, 1, 0), (4096, 128, 256, 1, 0),
+                                                  (777, 64, 128, 0, 1), (65536, 256, 512, 1, 0), (300, 512, 256, 0, 1)])
+def test_tensor_core_linear_3xtf32_vs_float64(m, n, k, relu, use_mask):
+    """tcgen05 kind::tf32 with hi/lo split: fp32-class accuracy (plain TF32 would be ~1e-3)."""
+    from beta_recsys_b200 import _lib
+
+    lib = _lib.load()
+    rng = np.random.default_rng(m + n + k)
+    x = rng.normal(0, 1, (m, k)).astype(np.float32)
+    w = (rng.normal(0, 1, (n, k)) / np.sqrt(k)).astype(np.float32)
+    b = rng.normal(0, 0.1, n).astype(np.float32)
+    msk = rng.normal(0, 1, (m, n)).astype(np.float32)
+    tx, tw, tb, tm = cuda(x, w, b, msk)
+    ty = torch.full((m, n), float("nan"), device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.check(lib.brs_mlp_fwd_tc(tx.data_ptr(), tw.data_ptr(), tb.data_ptr(), ty.data_ptr(),
+                                  tm.data_ptr() if use_mask else None, m, n, k, relu, st), "brs_mlp_fwd_tc")
+    want = x.astype(np.float64) @ w.T.astype(np.float64) + b
+    if relu:
+        want = np.maximum(want, 0)
+    if use_mask:
+        want = want * (msk > 0)
+    got = ty.cpu().numpy()
+    assert np.isfinite(got).all()
+    assert max_rel_err(got, want) <= 5e-6, max_rel_err(got, want)
+
+
+def test_neumf_same_result_on_both_gemm_backends():
+    from beta_recsys_b200 import _lib
+
+    lib = _lib.load()
+    rng = np.random.default_rng(33)
+    nu, ni, emb, nl, bsz = 2000, 1500, 64, 3, 4096
+    p = random_state("neumf", rng, nu, ni, emb, nl)
+    u, i = rng.integers(0, nu, bsz), rng.integers(0, ni, bsz)
+    r = (rng.random(bsz) < 0.2).astype(np.float32)
+    res = []
+    try:
+        for backend in (0, 1):
+            lib.brs_set_gemm_backend(backend)
+            eng = make_engine("neumf", nu, ni, emb, nl, bsz, "sgd", 0.05, state=p)
+            loss = eng.train_single_batch(*cuda(u, i, r))
+            res.append((loss, snap(eng)))
+    finally:
+        lib.brs_set_gemm_backend(1)
+    assert abs(res[0][0] - res[1][0]) <= 1e-6
+    for k in res[0][1]:
+        assert max_rel_err(res[1][1][k], res[0][1][k]) <= BUDGET, (k, max_rel_err(res[1][1][k], res[0][1][k]))
