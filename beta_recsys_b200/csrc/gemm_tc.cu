@@ -33,6 +33,24 @@ __device__ __forceinline__ float to_tf32(float x) {
     return __uint_as_float(u);
 }
 
+// mbarrier wait that traps instead of hanging the GPU if the tensor-core pipeline never signals
+__device__ __forceinline__ void mbar_wait_or_trap(uint64_t* bar, unsigned parity) {
+    for (unsigned spins = 0; spins < (1u << 26); ++spins) {
+        unsigned ok;
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (ok) return;
+    }
+    __trap();
+}
+
 // shared-memory matrix descriptor, SWIZZLE_NONE, K-major:
 //   start address >> 4 | LBO >> 4 at bit 16 | SBO >> 4 at bit 32 | version 1 at bit 46
 __device__ __forceinline__ unsigned long long make_smem_desc(unsigned smem_addr, unsigned lbo_bytes, unsigned sbo_bytes) {
@@ -142,7 +160,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) linear_tc_kernel(const TcArgs a
         float* b_hi = a_lo + A_FLOATS;
         float* b_lo = b_hi + B_FLOATS;
         if (kb >= TC_STAGES) {  // the MMAs that read this stage two k-blocks ago must be done
-            mbar_wait(&s_bar[s], (stage_phase >> s) & 1u);
+            mbar_wait_or_trap(&s_bar[s], (stage_phase >> s) & 1u);
             stage_phase ^= 1u << s;
         }
         stage_tile<TC_M>(a.A, a.lda, m0, a.M, kb * TC_BK, a_hi, a_lo);
@@ -168,7 +186,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) linear_tc_kernel(const TcArgs a
             if (kb == n_kb - 1) tc_commit(&s_done);     // accumulator complete
         }
     }
-    mbar_wait(&s_done, 0u);
+    mbar_wait_or_trap(&s_done, 0u);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
     // epilogue: warp w owns TMEM lanes [32w, 32w+32) = output rows m0 + 32w + lane
