@@ -275,8 +275,17 @@ def run_sharded(a, rank, world, local, dev):
         return users[s], pos[s], neg[s]
 
     def run_steps(k0, k):
-        for i in range(k0, k0 + k):
-            eng.launch_step(batch(i), out=outs[i % N_PREBUILT])
+        if a.route != "none":
+            for i in range(k0, k0 + k):
+                eng.launch_step(batch(i), out=outs[i % N_PREBUILT])
+            return
+        done, b = 0, k0 % N_PREBUILT
+        while done < k:  # one C call per pass over the prebuilt ring
+            nb = min(k - done, N_PREBUILT - b)
+            s = slice(b * a.batch, (b + nb) * a.batch)
+            outs[b:b + nb] = eng.train_batches(users[s], pos[s], neg[s])
+            done += nb
+            b = (b + nb) % N_PREBUILT
 
     def barrier():
         dist.barrier()

@@ -146,6 +146,8 @@ _PROTOTYPES = {
     "brs_ipc_close_handle": (C.c_int, [_P]),
     "brs_peer_barrier": (C.c_int, [C.POINTER(PeerSync), C.c_uint64, _P, _P]),
     "brs_mf_sharded_bpr_fwd_bwd": (C.c_int, [C.POINTER(MfSharded), _P, _P, _P, C.c_int64, C.c_int64, C.c_float, _P]),
+    "brs_mf_sharded_train_batches": (C.c_int, [C.POINTER(MfSharded), C.POINTER(PeerSync), C.POINTER(Opt), _P, _P, _P,
+                                               C.c_int64, C.c_int64, C.c_int64, C.c_float, C.c_uint64, _P, _P]),
     "brs_route_triples": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, _P, _P, _P, _P, _P]),
     "brs_gather": (C.c_int, [_P, C.c_int64, C.c_int32, _P, C.c_int64, _P, _P]),
     "brs_scatter_add": (C.c_int, [_P, C.c_int64, C.c_int32, _P, C.c_int64, _P, C.c_float, _P]),

@@ -124,6 +124,30 @@ extern "C" int brs_mf_train_batches(const brs_mf_model* model, const brs_opt* op
     return BRS_OK;
 }
 
+// the sharded epoch inner loop: every rank calls it with ITS OWN index arrays (same n / batch on all ranks)
+extern "C" int brs_mf_sharded_train_batches(const brs_mf_sharded* model, const brs_peer_sync* sync, const brs_opt* opt,
+                                            const int64_t* users, const int64_t* pos_items, const int64_t* neg_items,
+                                            int64_t n, int64_t batch, int64_t global_batch, float reg_weight,
+                                            uint64_t first_epoch, float* out, void* stream) {
+    if (!model || !sync || !opt || !users || !pos_items || !neg_items || !out || n < 0 || batch <= 0 || first_epoch == 0)
+        return BRS_ERR_INVALID_ARG;
+    uint64_t epoch = first_epoch;
+    int64_t b = 0;
+    for (int64_t off = 0; off < n; off += batch, ++b) {
+        const int64_t cur = (n - off < batch) ? (n - off) : batch;
+        const int64_t gb = (cur == batch) ? global_batch : cur * model->world;
+        int rc = brs_mf_sharded_bpr_fwd_bwd(model, users + off, pos_items + off, neg_items + off, cur, gb, reg_weight, stream);
+        if (rc != BRS_OK) return rc;
+        rc = brs_peer_barrier(sync, epoch++, model->local.ws, stream);
+        if (rc != BRS_OK) return rc;
+        rc = brs_mf_apply(&model->local, opt, gb, out + 4 * b, stream);
+        if (rc != BRS_OK) return rc;
+        rc = brs_peer_barrier(sync, epoch++, nullptr, stream);
+        if (rc != BRS_OK) return rc;
+    }
+    return BRS_OK;
+}
+
 // ---------------------------------------------------------------------------
 // gather / scatter-add micro-ops (config 5): warp-group per index, 128-bit accesses
 // ---------------------------------------------------------------------------

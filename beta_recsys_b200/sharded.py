@@ -316,6 +316,22 @@ class ShardedMFEngine(object):
                                          _lib.ptr(self._out if out is None else out), self._stream()), "brs_mf_apply")
         self._barrier(with_sums=False)  # every shard updated before anyone gathers again
 
+    def train_batches(self, users, pos, neg):
+        """Many consecutive steps over this rank's index arrays (route='none'): one C call, five
+        launches per batch, no host involvement until the caller reads the returned records."""
+        if self.route != "none":
+            raise _lib.BrsError("train_batches needs route='none' (routing needs a host round trip per batch)")
+        users, pos, neg = (as_index(x, self.device) for x in (users, pos, neg))
+        n, b = users.numel(), self.batch_size
+        n_batches = (n + b - 1) // b
+        out = torch.zeros((n_batches, 4), dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.brs_mf_sharded_train_batches(
+            C.byref(self._cmodel), C.byref(self._sync), C.byref(self.opt), _lib.ptr(users), _lib.ptr(pos), _lib.ptr(neg),
+            n, b, b * self.world, float(self.reg), self._epoch + 1, _lib.ptr(out), self._stream()),
+            "brs_mf_sharded_train_batches")
+        self._epoch += 2 * n_batches
+        return out
+
     def train_single_batch(self, batch, global_batch=None):
         self.launch_step(batch, global_batch)
         loss, reg, status, _ = self._out.tolist()

@@ -365,6 +365,14 @@ int brs_mf_sharded_bpr_fwd_bwd(const brs_mf_sharded *model, const int64_t *users
                                const int64_t *neg_items, int64_t batch, int64_t global_batch, float reg_weight,
                                void *stream);
 
+/* the sharded epoch inner loop over this rank's index arrays resident in HBM (same n and batch on every rank):
+ * per batch fwd_bwd, barrier(+sums), apply, barrier; barrier epochs first_epoch, first_epoch+1, ...
+ * (2 per batch); out = brs_step_out[ceil(n/batch)] */
+int brs_mf_sharded_train_batches(const brs_mf_sharded *model, const brs_peer_sync *sync, const brs_opt *opt,
+                                 const int64_t *users, const int64_t *pos_items, const int64_t *neg_items, int64_t n,
+                                 int64_t batch, int64_t global_batch, float reg_weight, uint64_t first_epoch,
+                                 float *out /* brs_step_out[] */, void *stream);
+
 /* stable bucket of (u,i,j) triples by owner(u) = u mod world (the send buffer of the NCCL all-to-all that
  * routes triples to the user-row owner): out_* hold the triples grouped by destination, original order
  * kept inside a group; counts[world] (device int64) receives the group sizes */
