@@ -47,7 +47,8 @@ class DenseParam(C.Structure):
 
 
 class MfModel(C.Structure):
-    _fields_ = [("user", Entity), ("item", Entity), ("global_bias", DenseParam), ("ws", C.c_void_p)]
+    _fields_ = [("user", Entity), ("item", Entity), ("global_bias", DenseParam), ("ws", C.c_void_p),
+                ("user_rows_alt", Rowset), ("item_rows_alt", Rowset)]
 
 
 NCF_GMF, NCF_MLP, NCF_NEUMF = 0, 1, 2

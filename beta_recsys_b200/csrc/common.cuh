@@ -16,7 +16,8 @@ struct __align__(16) brs_step_ws {
     unsigned int ticket;      // blocks finished in the apply kernel (last one finalises)
     long long step;           // optimizer step counter t (incremented by apply)
     unsigned int err_flag;    // set when an index is out of range
-    unsigned int pad_[9];
+    unsigned int err_pending[2];  // same, raised by a pre-pass that ran inside the PREVIOUS step's apply launch
+    unsigned int pad_[7];
 };
 static_assert(sizeof(brs_step_ws) <= BRS_STEP_WS_BYTES, "ws layout");
 

@@ -39,18 +39,19 @@ struct AssignArgs {
 // grid = (blocks, n_arrays): every block works on ONE index array, so all of its claims go to
 // one rowset and are aggregated into a single atomicAdd on that rowset's counter (the v1
 // per-thread atomicAdd on one address was 55% of this kernel's stall samples).
-__global__ void __launch_bounds__(kThreads) assign_slots_kernel(const AssignArgs a) {
+// body shared by the stand-alone pre-pass and by the apply kernel's "prepare the next batch" blocks:
+// block `bx` of `nbx` works on index array k
+__device__ __forceinline__ void assign_slots_block(const AssignArgs& a, int k, int bx, int nbx) {
     __shared__ int s_warp_cnt[kWarps];
     __shared__ int s_base;
-    const int k = blockIdx.y;
     const brs_rowset rs = a.rs[k];
     const long long* __restrict__ idx = a.idx[k];
     const long long n = a.n[k];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long stride = (long long)gridDim.x * kThreads;
+    const long long stride = (long long)nbx * kThreads;
     const long long n_iter = (n + stride - 1) / stride;
     for (long long it = 0; it < n_iter; ++it) {
-        const long long t = it * stride + (long long)blockIdx.x * kThreads + threadIdx.x;
+        const long long t = it * stride + (long long)bx * kThreads + threadIdx.x;
         long long row = -1;
         bool won = false;
         if (t < n) {
@@ -91,6 +92,10 @@ __global__ void __launch_bounds__(kThreads) assign_slots_kernel(const AssignArgs
         }
         __syncthreads();  // s_warp_cnt / s_base are reused by the next iteration
     }
+}
+
+__global__ void __launch_bounds__(kThreads) assign_slots_kernel(const AssignArgs a) {
+    assign_slots_block(a, blockIdx.y, blockIdx.x, gridDim.x);
 }
 
 // ---------------------------------------------------------------------------
@@ -163,6 +168,11 @@ struct ApplyArgs {
     double inv_batch;
     int advance_step;   // last block: ws->step += 1, reset sums
     int pol_scratch, pol_weight;  // L2 eviction policies (BRS_L2_*)
+    // optional: blocks [n_apply_blocks, gridDim.x) run the slot pre-pass of the NEXT batch (on the
+    // alternate rowsets) inside this launch -- both halves are latency-bound and overlap well
+    int n_apply_blocks;   // 0: every block applies
+    int parity;           // which ws->err_pending slot belongs to the batch being applied
+    AssignArgs next;
 };
 
 // one touched row of one table: scratch row `slot` -> weight row `row`
@@ -245,7 +255,7 @@ __device__ __forceinline__ void update_rows_small(const brs_table& tb, int cap, 
 template <int KIND>
 __device__ __forceinline__ void dense_params_update(const ApplyArgs& a, const OptScalars& s) {
     const long long tid = (long long)blockIdx.x * kThreads + threadIdx.x;
-    const long long nthreads = (long long)gridDim.x * kThreads;
+    const long long nthreads = (long long)(a.n_apply_blocks > 0 ? a.n_apply_blocks : gridDim.x) * kThreads;
     for (int k = (a.dense_grad_from_ws ? 1 : 0); k < a.n_dense; ++k) {
         const brs_dense_param& dp = a.dense[k];
         for (long long e = tid; e < dp.numel; e += nthreads) {
@@ -282,11 +292,13 @@ __device__ void finalize(const ApplyArgs& a, const OptScalars& s) {
         if (a.out) {  // brs_step_out
             a.out[0] = (float)(a.ws->loss_sum * a.inv_batch);
             a.out[1] = (float)(a.ws->reg_sum * a.inv_batch);
-            a.out[2] = (float)a.ws->err_flag;  // 0 ok | 1 index out of range | 2 touched-row capacity overflow
+            // 0 ok | 1 index out of range | 2 touched-row capacity overflow
+            a.out[2] = (float)(a.ws->err_flag | a.ws->err_pending[a.parity & 1]);
             a.out[3] = 0.f;
         }
         if (a.advance_step) {
             a.ws->err_flag = 0u;
+            a.ws->err_pending[a.parity & 1] = 0u;
             a.ws->loss_sum = 0.0;
             a.ws->reg_sum = 0.0;
             a.ws->g_global_bias = 0.f;
@@ -302,7 +314,7 @@ __device__ __forceinline__ bool last_block(const ApplyArgs& a) {
     __syncthreads();
     if (threadIdx.x == 0) {
         unsigned int prev = atomicAdd(&a.ws->ticket, 1u);
-        s_last = (prev == gridDim.x - 1);
+        s_last = (prev == (unsigned)(a.n_apply_blocks > 0 ? a.n_apply_blocks : gridDim.x) - 1);
     }
     __syncthreads();
     if (s_last) __threadfence();
@@ -318,6 +330,15 @@ __device__ __forceinline__ int clamped_count(const brs_rowset& rs) {
 template <int KIND>
 __global__ void __launch_bounds__(kThreads) rows_apply_kernel(const ApplyArgs a) {
     constexpr int ROWS = 4;
+    const int n_apply = a.n_apply_blocks > 0 ? a.n_apply_blocks : gridDim.x;
+    if ((int)blockIdx.x >= n_apply) {  // "prepare" role: slot pre-pass of the next batch
+        const int nb = gridDim.x - n_apply;          // blocks shared by the index arrays
+        const int per = nb / a.next.n_arrays;        // launch guarantees per >= 1
+        const int q = blockIdx.x - n_apply;
+        const int k = q / per;
+        if (k < a.next.n_arrays) assign_slots_block(a.next, k, q - k * per, per);
+        return;
+    }
     __shared__ OptScalars s_opt;
     __shared__ int s_cnt[kMaxEntities + 1];  // prefix of work items (groups of ROWS slots)
     __shared__ int s_rows[kMaxEntities];     // touched rows per entity
@@ -338,7 +359,7 @@ __global__ void __launch_bounds__(kThreads) rows_apply_kernel(const ApplyArgs a)
     const int lane = threadIdx.x & 31;
     const int warp = __shfl_sync(BRS_FULL_MASK, threadIdx.x >> 5, 0);
     const int total = s_cnt[a.n_ent];
-    for (int r = blockIdx.x * kWarps + warp; r < total; r += gridDim.x * kWarps) {
+    for (int r = blockIdx.x * kWarps + warp; r < total; r += n_apply * kWarps) {
         int e = 0;
         while (e + 1 < a.n_ent && r >= s_cnt[e + 1]) ++e;
         const brs_entity& en = a.ent[e];
@@ -512,7 +533,19 @@ int launch_apply(const ApplyArgs& a, int mode, long long max_rows_hint, cudaStre
         for (int d = 0; d < a.n_dense; ++d) need = max(need, (long long)((a.dense[d].numel + kThreads - 1) / kThreads));
         if (need < 1) need = 1;
         if (grid > need) grid = (int)need;
-        k<<<grid, kThreads, 0, st>>>(a);
+        if (a.next.n_arrays > 0) {  // fused "apply batch t + prepare batch t+1" launch
+            ApplyArgs b = a;
+            long long nmax = 0;
+            for (int q = 0; q < a.next.n_arrays; ++q) nmax = max(nmax, a.next.n[q]);
+            long long per = (nmax + kThreads - 1) / kThreads;
+            const long long cap = (long long)brs_sm_count() * 2;
+            if (per > cap) per = cap;
+            if (per < 1) per = 1;
+            b.n_apply_blocks = grid;
+            k<<<grid + (int)per * a.next.n_arrays, kThreads, 0, st>>>(b);
+        } else {
+            k<<<grid, kThreads, 0, st>>>(a);
+        }
         if (!a.ws) rowset_reset_counts_kernel<<<1, 32, 0, st>>>(a);  // stand-alone use: no last-block finalize
     }
     BRS_CUDA_CHECK(cudaGetLastError());
@@ -593,9 +626,24 @@ int brs_assign_slots(const brs_rowset* rs, const long long* const* idx, const lo
 }
 
 // shared with abi.cu: apply `opt` to entities + dense params (+ finalize through ws)
+int brs_apply_impl_next(const brs_entity* ents, int n_ent, const brs_dense_param* dense, int n_dense,
+                        int dense_grad_from_ws, const brs_opt* opt, void* ws, long long t_explicit, float* out,
+                        long long batch, long long max_rows_hint, void* stream, const brs_rowset* next_rs,
+                        const long long* const* next_idx, const long long* next_n, int next_arrays, int parity);
+
 int brs_apply_impl(const brs_entity* ents, int n_ent, const brs_dense_param* dense, int n_dense,
                    int dense_grad_from_ws, const brs_opt* opt, void* ws, long long t_explicit, float* out,
                    long long batch, long long max_rows_hint, void* stream) {
+    return brs_apply_impl_next(ents, n_ent, dense, n_dense, dense_grad_from_ws, opt, ws, t_explicit, out, batch,
+                               max_rows_hint, stream, nullptr, nullptr, nullptr, 0, 0);
+}
+
+// as brs_apply_impl; with next_arrays > 0 (touched-rows optimizers only) the same launch also runs the slot
+// pre-pass of the NEXT batch on the rowsets next_rs[k] (which must differ from the ones being applied)
+int brs_apply_impl_next(const brs_entity* ents, int n_ent, const brs_dense_param* dense, int n_dense,
+                        int dense_grad_from_ws, const brs_opt* opt, void* ws, long long t_explicit, float* out,
+                        long long batch, long long max_rows_hint, void* stream, const brs_rowset* next_rs,
+                        const long long* const* next_idx, const long long* next_n, int next_arrays, int parity) {
     if (!opt) return BRS_ERR_INVALID_ARG;
     int rc = validate_entities(ents, n_ent, opt->kind);
     if (rc != BRS_OK) return rc;
@@ -616,6 +664,20 @@ int brs_apply_impl(const brs_entity* ents, int n_ent, const brs_dense_param* den
     a.advance_step = ws ? 1 : 0;
     a.pol_scratch = brs_l2_cfg().scratch;
     a.pol_weight = brs_l2_cfg().weight;
+    if (next_arrays > 0) {
+        if (next_arrays > kMaxAssign || !ws || !next_rs || !next_idx || !next_n) return BRS_ERR_INVALID_ARG;
+        if (opt->kind != BRS_SGD && opt->mode == BRS_DENSE) return BRS_ERR_INVALID_ARG;  // the sweep reads slot maps
+        for (int k = 0; k < next_arrays; ++k) {
+            if (!next_rs[k].slot_map || !next_rs[k].list || !next_rs[k].count || !next_idx[k] || next_n[k] < 0)
+                return BRS_ERR_INVALID_ARG;
+            a.next.rs[k] = next_rs[k];
+            a.next.idx[k] = next_idx[k];
+            a.next.n[k] = next_n[k];
+        }
+        a.next.n_arrays = next_arrays;
+        a.next.err_flag = &((brs_step_ws*)ws)->err_pending[(parity + 1) & 1];
+    }
+    a.parity = parity & 1;
     cudaStream_t st = (cudaStream_t)stream;
     switch (opt->kind) {
         case BRS_SGD: return launch_apply<BRS_SGD>(a, BRS_TOUCHED_ROWS, max_rows_hint, st);

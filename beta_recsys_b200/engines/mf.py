@@ -93,7 +93,7 @@ class MFEngine(ModelEngine):
     def _refresh_struct(self):
         self._cmodel = _lib.MfModel(self._user.struct, self._item.struct,
                                     dense_param(self.model.global_bias.data, None, self._gb_state),
-                                    _lib.ptr(self._ws))
+                                    _lib.ptr(self._ws), self._user.alt_rowset(), self._item.alt_rowset())
 
     def _ensure_capacity(self, b):
         grew = self._user.ensure_capacity(b)

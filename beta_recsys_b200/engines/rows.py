@@ -20,14 +20,23 @@ class EntityState(object):
         for name, w in tables:
             assert w.is_cuda and w.dtype == torch.float32 and w.is_contiguous() and w.shape[0] == self.n_rows
             self.states.append(optimizer.add_param(name, w))
+        # alternate bookkeeping (slot map / list / counter) so that the epoch loop can claim slots for
+        # batch b+1 while batch b is being applied; the gradient scratch itself is shared
+        self.slot_map_alt = torch.full((self.n_rows,), -1, dtype=torch.int32, device=device)
+        self.count_alt = torch.zeros(1, dtype=torch.int32, device=device)
         self._alloc_scratch()
         self.struct = self._make_struct()
+
+    def alt_rowset(self):
+        return _lib.Rowset(_lib.ptr(self.slot_map_alt), _lib.ptr(self.list_alt), _lib.ptr(self.count_alt), self.n_rows,
+                           self.capacity, 0)
 
     def _alloc_scratch(self):
         """Compact gradient scratch [capacity, dim] per table + the slot list: the only
         per-step gradient storage (the reference materialises table-sized dense grads)."""
         dev = self.slot_map.device
         self.list = torch.zeros(self.capacity, dtype=torch.int32, device=dev)
+        self.list_alt = torch.zeros(self.capacity, dtype=torch.int32, device=dev)
         self.grads = [torch.zeros((self.capacity, w.shape[1]), dtype=torch.float32, device=dev) for w in self.weights]
 
     def _make_struct(self):

@@ -266,7 +266,7 @@ class ShardedMFEngine(object):
         gb = self.state["global_bias"]
         local = _lib.MfModel(entity("user", lu, self.cap_u), entity("item", li, self.cap_i),
                              _lib.DenseParam(_lib.ptr(self.global_bias), None, _lib.ptr(gb.get("m")),
-                                             _lib.ptr(gb.get("v")), 1), A.ptr("ws"))
+                                             _lib.ptr(gb.get("v")), 1), A.ptr("ws"), _lib.Rowset(), _lib.Rowset())
         peers = (_lib.MfPeerTables * w)()
         for r in range(w):
             for f, _ in _lib.MfPeerTables._fields_:

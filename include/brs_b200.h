@@ -124,6 +124,9 @@ typedef struct brs_mf_model {
     brs_entity item;              /* table[0] = item_emb [I,D], table[1] = item_bias [I,1] */
     brs_dense_param global_bias;  /* numel 1 */
     void *ws;                     /* BRS_STEP_WS_BYTES of device scratch */
+    /* optional second set of slot maps / lists / counters (same capacities; slot_map NULL = absent).  With
+     * them brs_mf_train_batches runs the slot pre-pass of batch b+1 inside the apply launch of batch b. */
+    brs_rowset user_rows_alt, item_rows_alt;
 } brs_mf_model;
 
 /* one rank's MF shard as seen from the calling process (pointers mapped through CUDA IPC / NVLink peer
