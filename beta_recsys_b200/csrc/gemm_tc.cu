@@ -11,7 +11,13 @@
 // registers into hi = tf32(x) and lo = tf32(x - hi); the MMA issuer then accumulates
 // hi.hi + hi.lo + lo.hi into the SAME TMEM accumulator (three tcgen05.mma per k-step).
 //
-// Structure (one CTA = one 128 x BN output tile, 128 threads):
+// Accuracy note (round-1 measurement, tools/gemm_accuracy.py): with ONE accumulator the error grew
+// linearly in K (rms 1.0e-6 / 1.9e-6 / 3.6e-6 at K = 128 / 256 / 512) -- the tensor core truncates on
+// every accumulation, a bias that adds up along the chain.  The kernel therefore keeps THREE TMEM
+// accumulators per tile -- hi.hi of the even k-blocks, hi.hi of the odd k-blocks, and the (2^-11
+// smaller) cross terms -- and adds them with round-to-nearest in the epilogue.
+//
+// Structure (one CTA = one 128 x BN output tile, 256 threads):
 //   * operands are written to shared memory in the canonical no-swizzle K-major core-matrix layout
 //     (8 rows x 16 bytes per core matrix) -- plain st.shared, no tensor maps needed;
 //   * thread 0 issues tcgen05.mma.cta_group::1.kind::tf32 (UMMA 128 x BN x 8), accumulator in TMEM;
@@ -24,7 +30,7 @@ namespace {
 
 constexpr int TC_M = 128;      // rows per CTA tile (UMMA_M)
 constexpr int TC_BK = 32;      // fp32 elements of K per stage (4 MMA k-steps of 8)
-constexpr int TC_THREADS = 128;
+constexpr int TC_THREADS = 256;
 constexpr int TC_STAGES = 2;
 
 __device__ __forceinline__ float to_tf32(float x) {
@@ -95,10 +101,17 @@ __device__ __forceinline__ int tile_off(int rows, int row, int k4) { return k4 *
 template <int ROWS>
 __device__ __forceinline__ void stage_tile(const float* __restrict__ src, int ld, int row0, int n_rows_total, int k0,
                                            float* __restrict__ hi, float* __restrict__ lo) {
+    // a quarter-warp covers the 8 rows of one core-matrix column (128 contiguous bytes of shared memory:
+    // conflict-free stores); the four quarter-warps take four adjacent 16-byte k chunks of the same rows
+    // (two full 32-byte sectors per row on the global side)
     const int t = threadIdx.x;
-    const int k4 = t & 7;  // which float4 of the 32-float row slice
-#pragma unroll 4
-    for (int r = t >> 3; r < ROWS; r += TC_THREADS / 8) {
+    const int lane = t & 31, w = t >> 5;
+    const int rsub = lane & 7, ksub = lane >> 3;
+    constexpr int NW = TC_THREADS / 32;
+#pragma unroll 2
+    for (int it = w; it < (ROWS / 8) * 2; it += NW) {
+        const int r = (it >> 1) * 8 + rsub;
+        const int k4 = (it & 1) * 4 + ksub;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         const int gr = row0 + r;
         if (gr < n_rows_total) v = *(const float4*)(src + (size_t)gr * ld + k0 + k4 * 4);
@@ -139,8 +152,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) linear_tc_kernel(const TcArgs a
         mbar_init(&s_done, 1);
         mbar_fence_init();
     }
-    if (warp == 0) {  // TMEM: BN fp32 accumulator columns (power of two >= 32)
-        constexpr unsigned cols = BN < 32 ? 32 : BN;
+    if (warp == 0) {  // TMEM: three BN-column fp32 accumulators (hi.hi even k-blocks, hi.hi odd, cross terms)
+        constexpr unsigned cols = 512;
+        static_assert(3 * BN <= 512, "TMEM columns");
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "n"(cols)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -178,9 +192,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) linear_tc_kernel(const TcArgs a
                 const unsigned long long al = make_smem_desc(a_lo_s + a_off, TC_M * 16, 128);
                 const unsigned long long bh = make_smem_desc(b_hi_s + b_off, BN * 16, 128);
                 const unsigned long long bl = make_smem_desc(b_lo_s + b_off, BN * 16, 128);
-                tc_mma_tf32(tmem_acc, ah, bh, idesc, (kb | j) ? 1u : 0u);
-                tc_mma_tf32(tmem_acc, ah, bl, idesc, 1u);
-                tc_mma_tf32(tmem_acc, al, bh, idesc, 1u);
+                tc_mma_tf32(tmem_acc + (unsigned)((kb & 1) * BN), ah, bh, idesc, ((kb >> 1) | j) ? 1u : 0u);
+                tc_mma_tf32(tmem_acc + (unsigned)(2 * BN), ah, bl, idesc, (kb | j) ? 1u : 0u);
+                tc_mma_tf32(tmem_acc + (unsigned)(2 * BN), al, bh, idesc, 1u);
             }
             tc_commit(&s_bar[s]);                       // stage s reusable once these MMAs finish
             if (kb == n_kb - 1) tc_commit(&s_done);     // accumulator complete
@@ -189,26 +203,40 @@ __global__ void __launch_bounds__(TC_THREADS, 1) linear_tc_kernel(const TcArgs a
     mbar_wait_or_trap(&s_done, 0u);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-    // epilogue: warp w owns TMEM lanes [32w, 32w+32) = output rows m0 + 32w + lane
-    const int row = m0 + warp * 32 + lane;
-    const unsigned taddr_row = tmem_acc + ((unsigned)(warp * 32) << 16);
+    // epilogue: a warp may only touch the TMEM lane quarter (warp % 4); the two warps of a quarter
+    // split the columns.  y = acc_even + acc_odd + acc_cross, then bias / ReLU / mask.
+    const int q = warp & 3, half = warp >> 2;
+    const int row = m0 + q * 32 + lane;
+    const unsigned taddr_row = tmem_acc + ((unsigned)(q * 32) << 16);
+    const bool have_odd = n_kb > 1;
 #pragma unroll 1
-    for (int c = 0; c < BN; c += 8) {
-        unsigned r[8];
+    for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += 8) {
+        unsigned r0[8], r1[8], r2[8];
         asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                     : "=r"(r0[0]), "=r"(r0[1]), "=r"(r0[2]), "=r"(r0[3]), "=r"(r0[4]), "=r"(r0[5]), "=r"(r0[6]), "=r"(r0[7])
                      : "r"(taddr_row + (unsigned)c));
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(r2[0]), "=r"(r2[1]), "=r"(r2[2]), "=r"(r2[3]), "=r"(r2[4]), "=r"(r2[5]), "=r"(r2[6]), "=r"(r2[7])
+                     : "r"(taddr_row + (unsigned)(2 * BN + c)));
+        if (have_odd) {
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                         : "=r"(r1[0]), "=r"(r1[1]), "=r"(r1[2]), "=r"(r1[3]), "=r"(r1[4]), "=r"(r1[5]), "=r"(r1[6]), "=r"(r1[7])
+                         : "r"(taddr_row + (unsigned)(BN + c)));
+        } else {
+#pragma unroll
+            for (int z = 0; z < 8; ++z) r1[z] = 0u;
+        }
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         if (row < a.M) {
             float v[8];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const int col = n0 + c + q;
-                float x = __uint_as_float(r[q]);
+            for (int z = 0; z < 8; ++z) {
+                const int col = n0 + c + z;
+                float x = (__uint_as_float(r0[z]) + __uint_as_float(r1[z])) + __uint_as_float(r2[z]);
                 if (a.bias) x += __ldg(a.bias + col);
                 if (a.relu) x = fmaxf(x, 0.f);
                 if (a.mask) x = (a.mask[(size_t)row * a.ldm + col] > 0.f) ? x : 0.f;
-                v[q] = x;
+                v[z] = x;
             }
             float* y = a.Y + (size_t)row * a.ldy + n0 + c;
             *(float4*)y = make_float4(v[0], v[1], v[2], v[3]);
@@ -218,7 +246,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) linear_tc_kernel(const TcArgs a
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0) {
-        constexpr unsigned cols = BN < 32 ? 32 : BN;
+        constexpr unsigned cols = 512;
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "n"(cols) : "memory");
     }
 }
@@ -258,8 +286,7 @@ int brs_linear_tc(const float* A, const float* B, const float* bias, float* Y, c
     a.mask = mask; a.ldm = N;
     a.M = M; a.N_total = N; a.K = K;
     a.relu = relu ? 1 : 0;
-    if (N % 256 == 0) return launch_tc<256>(a, st);
-    if (N % 128 == 0) return launch_tc<128>(a, st);
+    if (N % 128 == 0) return launch_tc<128>(a, st);  // 3 accumulators x 128 columns of the 512 TMEM columns
     return launch_tc<64>(a, st);
 }
 
