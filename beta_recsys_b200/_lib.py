@@ -86,7 +86,7 @@ IPC_HANDLE_BYTES = 64
 class MfPeerTables(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "user_emb", "item_emb", "user_bias", "item_bias", "g_user_emb", "g_item_emb", "g_user_bias", "g_item_bias",
-        "user_slot", "item_slot", "user_list", "item_list", "user_count", "item_count")]
+        "user_bits", "item_bits")]
 
 
 class PeerSync(C.Structure):
@@ -96,7 +96,8 @@ class PeerSync(C.Structure):
 
 class MfSharded(C.Structure):
     _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("n_users", C.c_int64), ("n_items", C.c_int64),
-                ("local", MfModel), ("peers", C.c_void_p)]
+                ("local_users", C.c_int64), ("local_items", C.c_int64), ("stage", MfModel), ("peers", C.c_void_p),
+                ("own", MfPeerTables)]
 
 
 EXTRA_STRUCTS = {"brs_csr": Csr, "brs_lightgcn_model": LightGCNModel, "brs_ncf_model": NcfModel, "brs_mf_peer_tables": MfPeerTables, "brs_peer_sync": PeerSync,
@@ -147,6 +148,7 @@ _PROTOTYPES = {
     "brs_ipc_close_handle": (C.c_int, [_P]),
     "brs_peer_barrier": (C.c_int, [C.POINTER(PeerSync), C.c_uint64, _P, _P]),
     "brs_mf_sharded_bpr_fwd_bwd": (C.c_int, [C.POINTER(MfSharded), _P, _P, _P, C.c_int64, C.c_int64, C.c_float, _P]),
+    "brs_mf_sharded_apply": (C.c_int, [C.POINTER(MfSharded), C.POINTER(Opt), C.c_int64, _P, _P]),
     "brs_mf_sharded_train_batches": (C.c_int, [C.POINTER(MfSharded), C.POINTER(PeerSync), C.POINTER(Opt), _P, _P, _P,
                                                C.c_int64, C.c_int64, C.c_int64, C.c_float, C.c_uint64, _P, _P]),
     "brs_route_triples": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, _P, _P, _P, _P, _P]),

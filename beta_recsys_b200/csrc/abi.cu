@@ -185,9 +185,9 @@ extern "C" int brs_mf_sharded_train_batches(const brs_mf_sharded* model, const b
         const int64_t gb = (cur == batch) ? global_batch : cur * model->world;
         int rc = brs_mf_sharded_bpr_fwd_bwd(model, users + off, pos_items + off, neg_items + off, cur, gb, reg_weight, stream);
         if (rc != BRS_OK) return rc;
-        rc = brs_peer_barrier(sync, epoch++, model->local.ws, stream);
+        rc = brs_peer_barrier(sync, epoch++, model->stage.ws, stream);
         if (rc != BRS_OK) return rc;
-        rc = brs_mf_apply(&model->local, opt, gb, out + 4 * b, stream);
+        rc = brs_mf_sharded_apply(model, opt, gb, out + 4 * b, stream);
         if (rc != BRS_OK) return rc;
         rc = brs_peer_barrier(sync, epoch++, nullptr, stream);
         if (rc != BRS_OK) return rc;

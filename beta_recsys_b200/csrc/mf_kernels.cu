@@ -28,9 +28,6 @@
 
 int brs_assign_slots(const brs_rowset* rs, const long long* const* idx, const long long* n, int n_arrays,
                      brs_step_ws* ws, cudaStream_t st);
-int brs_assign_slots_sharded(const brs_mf_peer_tables* peers, int world_shift, int user_cap, int item_cap,
-                             long long n_users, long long n_items, const long long* users, const long long* pos,
-                             const long long* neg, long long n, brs_step_ws* ws, cudaStream_t st);
 
 namespace {
 
@@ -49,12 +46,8 @@ struct MfPeerTables {  // one rank's shard, as seen from this process (device-re
     float* g_item_emb;
     float* g_user_bias;
     float* g_item_bias;
-    int* user_slot;
-    int* item_slot;
-    int* user_list;
-    int* item_list;
-    int* user_count;
-    int* item_count;
+    unsigned int* user_bits;
+    unsigned int* item_bits;
 };
 static_assert(sizeof(MfPeerTables) == sizeof(brs_mf_peer_tables), "peer table layout is part of the ABI");
 
@@ -62,12 +55,6 @@ template <class T>
 __device__ __forceinline__ T* ldg_ptr(T* const* p) {
     return (T*)__ldg((const unsigned long long*)p);
 }
-__device__ __forceinline__ int ld_volatile_s32(const int* p) {
-    int v;
-    asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(v) : "l"(p));
-    return v;
-}
-
 struct MfArgs {
     const float* __restrict__ user_emb;
     const float* __restrict__ item_emb;
@@ -162,9 +149,6 @@ __device__ __forceinline__ void sample_load(const MfArgs& a, const IdxTile& T, i
         t_ub = ldg_ptr(&pu->user_bias);
         t_ib = ldg_ptr(&pi->item_bias);
         t_jb = ldg_ptr(&pj->item_bias);
-        t_us = ldg_ptr(&pu->user_slot);
-        t_is = ldg_ptr(&pi->item_slot);
-        t_js = ldg_ptr(&pj->item_slot);
     }
     // rows < 2^31 (slot maps are int32), so one 32x32->64 IMAD.WIDE per row address
     const float* ur = t_ue + (unsigned long long)lu * (unsigned)D;
@@ -181,17 +165,10 @@ __device__ __forceinline__ void sample_load(const MfArgs& a, const IdxTile& T, i
     x.bu = __ldg(t_ub + lu);
     x.bi = __ldg(t_ib + li);
     x.bj = (LOSS == LOSS_BPR) ? __ldg(t_jb + lj) : 0.f;
-    if (!SHARD) {
-        x.su = __ldg(t_us + lu);
-        x.si = __ldg(t_is + li);
-        x.sj = (LOSS == LOSS_BPR) ? __ldg(t_js + lj) : 0;
-    } else {
-        // another rank may still be publishing the slot it claimed for this row: poll past PENDING
-        do { x.su = ld_volatile_s32(t_us + lu); } while (x.su == BRS_SLOT_PENDING && x.valid);
-        do { x.si = ld_volatile_s32(t_is + li); } while (x.si == BRS_SLOT_PENDING && x.valid);
-        x.sj = 0;
-        if (LOSS == LOSS_BPR) do { x.sj = ld_volatile_s32(t_js + lj); } while (x.sj == BRS_SLOT_PENDING && x.valid);
-    }
+    // slots of the LOCAL compact scratch: indexed by the (global) id, assigned by this rank's pre-pass
+    x.su = __ldg(t_us + (unsigned)x.u);
+    x.si = __ldg(t_is + (unsigned)x.i);
+    x.sj = (LOSS == LOSS_BPR) ? __ldg(t_js + (unsigned)x.j) : 0;
     if (x.su < 0 || x.si < 0 || x.sj < 0) x.valid = false;  // capacity overflow, flagged by the pre-pass
 }
 
@@ -256,17 +233,10 @@ __device__ __forceinline__ void sample_finish(const MfArgs& a, const Sample<VPL,
         gb_acc += cu_i + cu_j;
     }
     const float rw = 2.0f * a.reg_w * a.inv_b;  // d(reg_w*regularizer)/d row = rw * row per forward call
+    // gradients always go to THIS rank's compact scratch (also under SHARD: they are pushed to the owners
+    // row by row afterwards, mf_push_kernel)
     float *t_gu = a.g_user_emb, *t_gi = a.g_item_emb, *t_gj = a.g_item_emb;
     float *t_gub = a.g_user_bias, *t_gib = a.g_item_bias, *t_gjb = a.g_item_bias;
-    if (SHARD) {  // the owners' gradient scratch: the REDs below travel over NVLink
-        const MfPeerTables *pu = a.peers + x.ou, *pi = a.peers + x.oi, *pj = a.peers + x.oj;
-        t_gu = ldg_ptr(&pu->g_user_emb);
-        t_gi = ldg_ptr(&pi->g_item_emb);
-        t_gj = ldg_ptr(&pj->g_item_emb);
-        t_gub = ldg_ptr(&pu->g_user_bias);
-        t_gib = ldg_ptr(&pi->g_item_bias);
-        t_gjb = ldg_ptr(&pj->g_item_bias);
-    }
     float* gu = t_gu;
     float* gi = t_gi;
     float* gj = t_gj;
@@ -673,6 +643,66 @@ extern "C" int brs_mf_predict(const brs_mf_model* model, const int64_t* users, c
     return BRS_OK;
 }
 
+
+// ---------------------------------------------------------------------------
+// multi-GPU: push this rank's aggregated gradient rows to the owners' dense shard gradients
+// ---------------------------------------------------------------------------
+namespace {
+
+struct PushArgs {
+    const MfPeerTables* __restrict__ peers;
+    brs_rowset rows[2];       // user / item rowsets (GLOBAL ids)
+    float* scratch_emb[2];    // local compact scratch (sector-blocked)
+    float* scratch_bias[2];
+    int dim, shift, mask;
+};
+
+__device__ __forceinline__ void red_or_u32(unsigned int* p, unsigned int v) {
+    asm volatile("red.relaxed.sys.global.or.b32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// one warp per touched slot: 128-bit REDs of the whole row into the owner's dense gradient table
+// (coalesced 16*lanes-byte bursts over NVLink), bias, touched bit; the local scratch row is zeroed
+// and the local slot released on the way.
+__global__ void __launch_bounds__(256) mf_push_kernel(const PushArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int D = a.dim;
+    const int cu = min(*a.rows[0].count, a.rows[0].capacity), ci = min(*a.rows[1].count, a.rows[1].capacity);
+    const int total = cu + ci;
+    for (int w = blockIdx.x * 8 + (threadIdx.x >> 5); w < total; w += gridDim.x * 8) {
+        const int e = w < cu ? 0 : 1;
+        const int s = e == 0 ? w : w - cu;
+        const brs_rowset& rs = a.rows[e];
+        const unsigned g = (unsigned)rs.list[s];
+        const int owner = (int)(g & (unsigned)a.mask);
+        const unsigned lrow = g >> a.shift;
+        const MfPeerTables* pt = a.peers + owner;
+        float* dst = (e == 0 ? ldg_ptr(&pt->g_user_emb) : ldg_ptr(&pt->g_item_emb)) + (size_t)lrow * (unsigned)D;
+        for (int c = lane * 4; c < D; c += 128) {
+            float* src = a.scratch_emb[e] + gs_off(D, rs.capacity, (unsigned)s, c);
+            const float4 v = *(const float4*)src;
+            red_add4(dst + c, v);
+            *(float4*)src = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (lane == 0) {
+            float* sb = a.scratch_bias[e] + s;
+            red_add1((e == 0 ? ldg_ptr(&pt->g_user_bias) : ldg_ptr(&pt->g_item_bias)) + lrow, *sb);
+            *sb = 0.f;
+            red_or_u32((e == 0 ? ldg_ptr(&pt->user_bits) : ldg_ptr(&pt->item_bits)) + (lrow >> 5), 1u << (lrow & 31));
+            rs.slot_map[g] = BRS_SLOT_NONE;
+        }
+    }
+}
+
+__global__ void mf_push_reset_kernel(int* c0, int* c1) {
+    if (threadIdx.x == 0) {
+        *c0 = 0;
+        *c1 = 0;
+    }
+}
+
+}  // namespace
+
 extern "C" int brs_mf_sharded_bpr_fwd_bwd(const brs_mf_sharded* model, const int64_t* users, const int64_t* pos_items,
                                           const int64_t* neg_items, int64_t batch, int64_t global_batch,
                                           float reg_weight, void* stream) {
@@ -681,12 +711,14 @@ extern "C" int brs_mf_sharded_bpr_fwd_bwd(const brs_mf_sharded* model, const int
     const int w = model->world;
     if (w < 1 || w > BRS_MAX_RANKS || (w & (w - 1)) != 0 || model->rank < 0 || model->rank >= w) return BRS_ERR_UNSUPPORTED;
     MfArgs a;
-    int rc = fill_args(&model->local, a, true);
+    int rc = fill_args(&model->stage, a, true);
     if (rc != BRS_OK) return rc;
+    if (model->stage.user.rows.n_rows != model->n_users || model->stage.item.rows.n_rows != model->n_items)
+        return BRS_ERR_INVALID_ARG;  // the staging slot maps are indexed by GLOBAL ids
     if (batch == 0) return BRS_OK;
     int shift = 0;
     while ((1 << shift) < w) ++shift;
-    a.n_users = model->n_users;  // GLOBAL ids are range-checked against the global sizes
+    a.n_users = model->n_users;
     a.n_items = model->n_items;
     a.peers = (const MfPeerTables*)model->peers;
     a.shard_shift = shift;
@@ -698,8 +730,28 @@ extern "C" int brs_mf_sharded_bpr_fwd_bwd(const brs_mf_sharded* model, const int
     a.reg_w = reg_weight;
     a.inv_b = 1.0f / (float)global_batch;
     cudaStream_t st = (cudaStream_t)stream;
-    rc = brs_assign_slots_sharded(model->peers, shift, a.user_cap, a.item_cap, model->n_users, model->n_items,
-                                  a.users, a.items, (const long long*)neg_items, batch, a.ws, st);
+    {   // local pre-pass over GLOBAL ids
+        const brs_rowset rs[3] = {model->stage.user.rows, model->stage.item.rows, model->stage.item.rows};
+        const long long* idx[3] = {a.users, a.items, (const long long*)neg_items};
+        const long long n[3] = {batch, batch, batch};
+        rc = brs_assign_slots(rs, idx, n, 3, a.ws, st);
+        if (rc != BRS_OK) return rc;
+    }
+    rc = launch_fwd_bwd<LOSS_BPR, true>(a, st);
     if (rc != BRS_OK) return rc;
-    return launch_fwd_bwd<LOSS_BPR, true>(a, st);
+    PushArgs p;
+    p.peers = a.peers;
+    p.rows[0] = model->stage.user.rows;
+    p.rows[1] = model->stage.item.rows;
+    p.scratch_emb[0] = a.g_user_emb;
+    p.scratch_emb[1] = a.g_item_emb;
+    p.scratch_bias[0] = a.g_user_bias;
+    p.scratch_bias[1] = a.g_item_bias;
+    p.dim = a.dim;
+    p.shift = shift;
+    p.mask = w - 1;
+    mf_push_kernel<<<brs_sm_count() * 4, 256, 0, st>>>(p);
+    mf_push_reset_kernel<<<1, 32, 0, st>>>(model->stage.user.rows.count, model->stage.item.rows.count);
+    BRS_CUDA_CHECK(cudaGetLastError());
+    return BRS_OK;
 }

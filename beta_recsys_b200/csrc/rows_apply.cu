@@ -474,6 +474,85 @@ __global__ void rowset_reset_counts_kernel(const ApplyArgs a) {
     if (threadIdx.x < a.n_ent) *a.ent[threadIdx.x].rows.count = 0;
 }
 
+// ---------------------------------------------------------------------------
+// multi-GPU owner side: apply the optimizer to the rows of this shard whose touched bit is set
+// (the gradients were pushed into the shard's DENSE gradient tables by all ranks, mf_push_kernel)
+// ---------------------------------------------------------------------------
+struct ShardEnt {
+    float* w; float* wb;      // shard weights [rows, dim], [rows]
+    float* g; float* gb;      // dense gradients, same shapes (row-major)
+    float* m; float* v; float* mb; float* vb;
+    unsigned int* bits;
+    long long rows;
+};
+struct ShardApplyArgs {
+    ShardEnt ent[2];
+    int dim;
+    int dense_all;   // 1: every row is updated (g = 0 where the bit is clear): reference-exact Adam / RMSprop
+    ApplyArgs base;  // opt, ws, out, inv_batch, global-bias dense param, finalize bookkeeping
+};
+
+template <int KIND>
+__global__ void __launch_bounds__(kThreads) shard_apply_kernel(const ShardApplyArgs a) {
+    __shared__ OptScalars s_opt;
+    if (threadIdx.x == 0) s_opt = make_scalars(a.base.opt, a.base.ws->step + 1);
+    __syncthreads();
+    const OptScalars s = s_opt;
+    const int lane = threadIdx.x & 31;
+    const int D = a.dim;
+    const long long words0 = (a.ent[0].rows + 31) >> 5, words1 = (a.ent[1].rows + 31) >> 5;
+    // a warp per bitmap word (32 rows)
+    for (long long wi = (long long)blockIdx.x * kWarps + (threadIdx.x >> 5); wi < words0 + words1;
+         wi += (long long)gridDim.x * kWarps) {
+        const ShardEnt& e = a.ent[wi < words0 ? 0 : 1];
+        const long long word = wi < words0 ? wi : wi - words0;
+        const unsigned int bits = e.bits[word];
+        unsigned int todo = bits;
+        if (a.dense_all) {
+            const long long left = e.rows - word * 32;
+            todo = left >= 32 ? 0xffffffffu : ((1u << left) - 1u);
+        }
+        while (todo) {
+            const int b = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const bool touched = (bits >> b) & 1u;
+            const long long row = word * 32 + b;
+            for (int c = lane * 4; c < D; c += 128) {
+                const size_t o = (size_t)row * D + c;
+                float4 gv = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (touched) {
+                    gv = *(const float4*)(e.g + o);
+                    *(float4*)(e.g + o) = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                float4 wv = *(const float4*)(e.w + o);
+                float4 mv = make_float4(0.f, 0.f, 0.f, 0.f), vv = mv;
+                if (KIND == BRS_ADAM) mv = *(const float4*)(e.m + o);
+                if (KIND != BRS_SGD) vv = *(const float4*)(e.v + o);
+                opt_elem4<KIND>(wv, gv, mv, vv, s);
+                *(float4*)(e.w + o) = wv;
+                if (KIND == BRS_ADAM) *(float4*)(e.m + o) = mv;
+                if (KIND != BRS_SGD) *(float4*)(e.v + o) = vv;
+            }
+            if (lane == 0) {
+                float g = 0.f;
+                if (touched) {
+                    g = e.gb[row];
+                    e.gb[row] = 0.f;
+                }
+                float w = e.wb[row];
+                float m = (KIND == BRS_ADAM) ? e.mb[row] : 0.f;
+                float v = (KIND != BRS_SGD) ? e.vb[row] : 0.f;
+                opt_elem<KIND>(w, g, m, v, s);
+                e.wb[row] = w;
+                if (KIND == BRS_ADAM) e.mb[row] = m;
+                if (KIND != BRS_SGD) e.vb[row] = v;
+            }
+        }
+        if (lane == 0 && bits) e.bits[word] = 0u;
+    }
+    if (last_block(a.base)) finalize<KIND>(a.base, s);
+}
+
 int validate_entities(const brs_entity* ents, int n, int kind) {
     if (n < 0 || n > kMaxEntities || (n > 0 && !ents)) return BRS_ERR_INVALID_ARG;
     for (int e = 0; e < n; ++e) {
@@ -721,4 +800,59 @@ extern "C" int brs_dense_params_step(const brs_dense_param* params, int32_t n_pa
     brs_opt o = *opt;
     o.mode = BRS_TOUCHED_ROWS;
     return brs_apply_impl(nullptr, 0, params, n_params, 0, &o, nullptr, t, nullptr, 0, 0, stream);
+}
+
+extern "C" int brs_mf_sharded_apply(const brs_mf_sharded* model, const brs_opt* opt, int64_t global_batch, float* out,
+                                    void* stream) {
+    if (!model || !opt || !model->stage.ws || global_batch <= 0) return BRS_ERR_INVALID_ARG;
+    const brs_mf_model& sm = model->stage;
+    const int D = sm.user.table[0].dim;
+    if (D <= 0 || (D & 3) != 0) return BRS_ERR_UNSUPPORTED;
+    ShardApplyArgs a;
+    memset(&a, 0, sizeof(a));
+    const brs_entity* ents[2] = {&sm.user, &sm.item};
+    const brs_mf_peer_tables& own = model->own;
+    float* g[2] = {own.g_user_emb, own.g_item_emb};
+    float* gb[2] = {own.g_user_bias, own.g_item_bias};
+    unsigned int* bits[2] = {own.user_bits, own.item_bits};
+    const long long rows[2] = {model->local_users, model->local_items};
+    for (int e = 0; e < 2; ++e) {
+        const brs_table& te = ents[e]->table[0];
+        const brs_table& tb = ents[e]->table[1];
+        if (!te.weight || !tb.weight || !g[e] || !gb[e] || !bits[e]) return BRS_ERR_INVALID_ARG;
+        if (opt->kind == BRS_ADAM && (!te.m || !te.v || !tb.m || !tb.v)) return BRS_ERR_INVALID_ARG;
+        if (opt->kind == BRS_RMSPROP && (!te.v || !tb.v)) return BRS_ERR_INVALID_ARG;
+        a.ent[e] = ShardEnt{te.weight, tb.weight, g[e], gb[e], te.m, te.v, tb.m, tb.v, bits[e], rows[e]};
+    }
+    a.dim = D;
+    a.dense_all = (opt->kind != BRS_SGD && opt->mode == BRS_DENSE) ? 1 : 0;
+    int rc = validate_dense(&sm.global_bias, 1, opt->kind, true);
+    if (rc != BRS_OK) return rc;
+    a.base.dense[0] = sm.global_bias;
+    a.base.n_dense = 1;
+    a.base.dense_grad_from_ws = 1;
+    fill_opt(a.base, opt);
+    a.base.ws = (brs_step_ws*)sm.ws;
+    a.base.out = out;
+    a.base.inv_batch = 1.0 / (double)global_batch;
+    a.base.advance_step = 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long words = ((rows[0] + 31) >> 5) + ((rows[1] + 31) >> 5);
+#define BRS_SHARD_APPLY(KIND)                                                         \
+    do {                                                                              \
+        auto k = shard_apply_kernel<KIND>;                                            \
+        long long grid = persistent_grid((const void*)k);                             \
+        const long long need = (words + kWarps - 1) / kWarps;                         \
+        if (grid > need) grid = need;                                                 \
+        k<<<(int)(grid < 1 ? 1 : grid), kThreads, 0, st>>>(a);                        \
+    } while (0)
+    switch (opt->kind) {
+        case BRS_SGD: BRS_SHARD_APPLY(BRS_SGD); break;
+        case BRS_ADAM: BRS_SHARD_APPLY(BRS_ADAM); break;
+        case BRS_RMSPROP: BRS_SHARD_APPLY(BRS_RMSPROP); break;
+        default: return BRS_ERR_UNSUPPORTED;
+    }
+#undef BRS_SHARD_APPLY
+    BRS_CUDA_CHECK(cudaGetLastError());
+    return BRS_OK;
 }

@@ -5,8 +5,8 @@
 // maps its peers', so the hot-path kernels address remote rows directly over NVLink
 // (peer loads / peer REDs / peer atomics) instead of staging them through collectives.
 // This file holds: the exportable allocator + IPC handle helpers, the flag barrier that
-// orders the phases of a step across ranks (and exchanges the step's scalar sums), the
-// sharded slot pre-pass, and the owner bucketing of triples that feeds the (optional)
+// orders the phases of a step across ranks (and exchanges the step's scalar sums), and the
+// owner bucketing of triples that feeds the (optional)
 // NCCL all-to-all routing of triples to the user-row owner.
 #include <string.h>
 
@@ -66,84 +66,6 @@ __global__ void __launch_bounds__(32) peer_barrier_kernel(const BarrierArgs a) {
         a.ws->reg_sum = r;
         a.ws->g_global_bias = (float)g;
         a.ws->err_flag = (unsigned int)e;
-    }
-}
-
-// ---------------------------------------------------------------------------
-// sharded slot pre-pass: claims go to the OWNER's slot map / list / counter (peer atomics)
-// ---------------------------------------------------------------------------
-struct ShardAssignArgs {
-    const brs_mf_peer_tables* peers;  // device array [world]
-    const long long* idx[3];
-    long long n;
-    long long n_rows[3];  // global table size per array (users, items, items)
-    int cap[3];
-    int world, shift;
-    unsigned int* err_flag;
-};
-
-__global__ void __launch_bounds__(kThreads) assign_slots_sharded_kernel(const ShardAssignArgs a) {
-    __shared__ int s_warp_cnt[kWarps][BRS_MAX_RANKS];
-    __shared__ int s_base[BRS_MAX_RANKS];
-    const int k = blockIdx.y;  // 0 users, 1 pos items, 2 neg items
-    const bool is_user = k == 0;
-    const long long* __restrict__ idx = a.idx[k];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long stride = (long long)gridDim.x * kThreads;
-    const long long n_iter = (a.n + stride - 1) / stride;
-    for (long long it = 0; it < n_iter; ++it) {
-        const long long t = it * stride + (long long)blockIdx.x * kThreads + threadIdx.x;
-        int owner = -1;
-        unsigned local = 0;
-        bool won = false;
-        int* slot_map = nullptr;
-        if (t < a.n) {
-            const long long row = idx[t];
-            if ((unsigned long long)row >= (unsigned long long)a.n_rows[k]) {
-                atomicOr(a.err_flag, 1u);
-            } else {
-                owner = (int)(row & (a.world - 1));
-                local = (unsigned)(row >> a.shift);
-                const brs_mf_peer_tables* pt = a.peers + owner;
-                slot_map = is_user ? pt->user_slot : pt->item_slot;
-                int cur;
-                asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(cur) : "l"(slot_map + local));
-                if (cur == BRS_SLOT_NONE) won = atomicCAS(slot_map + local, BRS_SLOT_NONE, BRS_SLOT_PENDING) == BRS_SLOT_NONE;
-            }
-        }
-        int lane_off = 0;
-        for (int o = 0; o < a.world; ++o) {  // one aggregated counter add per (block, owner)
-            const unsigned b = __ballot_sync(BRS_FULL_MASK, won && owner == o);
-            if (won && owner == o) lane_off = __popc(b & ((1u << lane) - 1u));
-            if (lane == 0) s_warp_cnt[warp][o] = __popc(b);
-        }
-        __syncthreads();
-        if (threadIdx.x < a.world) {
-            const int o = threadIdx.x;
-            int tot = 0;
-            for (int w = 0; w < kWarps; ++w) {
-                const int c = s_warp_cnt[w][o];
-                s_warp_cnt[w][o] = tot;
-                tot += c;
-            }
-            const brs_mf_peer_tables* pt = a.peers + o;
-            s_base[o] = tot ? atomicAdd(is_user ? pt->user_count : pt->item_count, tot) : 0;
-        }
-        __syncthreads();
-        if (won) {
-            const brs_mf_peer_tables* pt = a.peers + owner;
-            const int slot = s_base[owner] + s_warp_cnt[warp][owner] + lane_off;
-            int v = slot;
-            if (slot < a.cap[k]) {
-                (is_user ? pt->user_list : pt->item_list)[slot] = (int)local;
-            } else {
-                v = BRS_SLOT_NONE;
-                atomicOr(a.err_flag, 2u);
-            }
-            __threadfence_system();  // list entry before the slot becomes visible to pollers on other GPUs
-            asm volatile("st.volatile.global.s32 [%0], %1;" ::"l"(slot_map + local), "r"(v) : "memory");
-        }
-        __syncthreads();
     }
 }
 
@@ -278,33 +200,6 @@ extern "C" int brs_peer_barrier(const brs_peer_sync* sync, uint64_t epoch, void*
     a.epoch = epoch;
     a.ws = (brs_step_ws*)ws;
     peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(a);
-    BRS_CUDA_CHECK(cudaGetLastError());
-    return BRS_OK;
-}
-
-int brs_assign_slots_sharded(const brs_mf_peer_tables* peers, int world_shift, int user_cap, int item_cap,
-                             long long n_users, long long n_items, const long long* users, const long long* pos,
-                             const long long* neg, long long n, brs_step_ws* ws, cudaStream_t st) {
-    if (!peers || !users || !pos || !neg || !ws || n < 0) return BRS_ERR_INVALID_ARG;
-    if (n == 0) return BRS_OK;
-    ShardAssignArgs a;
-    memset(&a, 0, sizeof(a));
-    a.peers = peers;
-    a.idx[0] = users;
-    a.idx[1] = pos;
-    a.idx[2] = neg;
-    a.n = n;
-    a.n_rows[0] = n_users;
-    a.n_rows[1] = a.n_rows[2] = n_items;
-    a.cap[0] = user_cap;
-    a.cap[1] = a.cap[2] = item_cap;
-    a.shift = world_shift;
-    a.world = 1 << world_shift;
-    a.err_flag = &ws->err_flag;
-    long long blocks = (n + kThreads - 1) / kThreads;
-    const long long cap = (long long)brs_sm_count() * 4;
-    if (blocks > cap) blocks = cap;
-    assign_slots_sharded_kernel<<<dim3((unsigned)blocks, 3), kThreads, 0, st>>>(a);
     BRS_CUDA_CHECK(cudaGetLastError());
     return BRS_OK;
 }

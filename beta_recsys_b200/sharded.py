@@ -2,15 +2,17 @@
 
 New work -- the reference has no distributed path.  Tables are
 row-sharded: ``owner(row) = row mod world``, ``local row = row div world``.  Every rank
-exports its shard (tables, compact gradient scratch, slot maps) through CUDA IPC; the
-kernels then address remote rows directly over NVLink: gathers are peer loads, gradient
-scatters are peer REDs into the owner's scratch, slots are claimed with peer atomics.
-A step is
+exports its shard (weights, a dense per-shard gradient table, a touched bitmap) through
+CUDA IPC; the kernels address remote memory directly over NVLink.  A step is
 
     [optional NCCL all-to-all: route triples to the user-row owner]
-    slot pre-pass + fused fwd/bwd   (peer memory, no collective)
+    local slot pre-pass + fused fwd/bwd: rows gathered with peer loads, gradients summed in
+                                         a LOCAL compact scratch (no remote atomics per sample)
+    push: one coalesced row per unique touched row -> 128-bit peer REDs into the owner's dense
+          gradient table + red.or of its touched bit
     flag barrier  (+ exchange of the 3 step sums, added in rank order)
-    optimizer on the local shard     (global_bias is replicated and updated identically)
+    optimizer on the rows of the local shard whose bit is set (global_bias is replicated
+          and updated identically on every rank)
     flag barrier
 
 The loss is the mean over the GLOBAL batch (sum of the ranks' batches), exactly what a
@@ -192,23 +194,33 @@ class ShardedMFEngine(object):
         self.opt = _lib.make_opt(self.opt_kind, self.lr, _lib.DENSE if mode == "dense" else _lib.TOUCHED_ROWS)
         w, d = self.world, self.dim
         lu, li = local_rows(self.n_users, w), local_rows(self.n_items, w)
-        # a slot for every distinct row any rank can send here in one step
-        grow = 2 if route == "owner" else 1  # routed batches are uneven (Zipf users)
-        self.cap_u = int(max(1, min(lu, grow * w * self.batch_size)))
-        self.cap_i = int(max(1, min(li, 2 * grow * w * self.batch_size)))
+        self.local_users, self.local_items = lu, li
         f32, i32 = torch.float32, torch.int32
-        layout = [
+        layout = [  # peer-visible: shard weights, dense shard gradients, touched bitmaps, barrier state
             ("user_emb", (lu, d), f32), ("item_emb", (li, d), f32), ("user_bias", (lu, 1), f32),
-            ("item_bias", (li, 1), f32), ("g_user_emb", (self.cap_u * d,), f32), ("g_item_emb", (self.cap_i * d,), f32),
-            ("g_user_bias", (self.cap_u,), f32), ("g_item_bias", (self.cap_i,), f32), ("user_slot", (lu,), i32),
-            ("item_slot", (li,), i32), ("user_list", (self.cap_u,), i32), ("item_list", (self.cap_i,), i32),
-            ("user_count", (1,), i32), ("item_count", (1,), i32), ("flags", (_lib.MAX_RANKS,), torch.int64),
+            ("item_bias", (li, 1), f32), ("g_user_emb", (lu, d), f32), ("g_item_emb", (li, d), f32),
+            ("g_user_bias", (lu,), f32), ("g_item_bias", (li,), f32), ("user_bits", ((lu + 31) // 32,), i32),
+            ("item_bits", ((li + 31) // 32,), i32), ("flags", (_lib.MAX_RANKS,), torch.int64),
             ("partials", (_lib.MAX_RANKS * 4,), torch.float64), ("ws", (_lib.STEP_WS_BYTES,), torch.uint8),
         ]
         self.arena = PeerArena(layout, self.device, group)
         t = self.arena.tensor
-        t("user_slot").fill_(-1)
-        t("item_slot").fill_(-1)
+        # local staging (not peer-visible): slot maps over GLOBAL ids + compact gradient scratch
+        grow = 2 if route == "owner" else 1  # routed batches are uneven (Zipf users)
+        self.cap_u = int(max(1, min(self.n_users, grow * self.batch_size)))
+        self.cap_i = int(max(1, min(self.n_items, 2 * grow * self.batch_size)))
+        dev = self.device
+        self._stage = {
+            "user_slot": torch.full((self.n_users,), -1, dtype=i32, device=dev),
+            "item_slot": torch.full((self.n_items,), -1, dtype=i32, device=dev),
+            "user_list": torch.zeros(self.cap_u, dtype=i32, device=dev),
+            "item_list": torch.zeros(self.cap_i, dtype=i32, device=dev),
+            "user_count": torch.zeros(1, dtype=i32, device=dev), "item_count": torch.zeros(1, dtype=i32, device=dev),
+            "s_user_emb": torch.zeros(self.cap_u * d, dtype=f32, device=dev),
+            "s_item_emb": torch.zeros(self.cap_i * d, dtype=f32, device=dev),
+            "s_user_bias": torch.zeros(self.cap_u, dtype=f32, device=dev),
+            "s_item_bias": torch.zeros(self.cap_i, dtype=f32, device=dev),
+        }
         self.global_bias = torch.zeros(1, dtype=f32, device=self.device)  # replicated
         self._init_tables(state)
         # optimizer state: local only
@@ -247,24 +259,25 @@ class ShardedMFEngine(object):
             t("item_emb").normal_(0, 0.1, generator=g)
 
     def _build_structs(self):
-        A = self.arena
+        A, S = self.arena, self._stage
         w, d = self.world, self.dim
-        lu, li = local_rows(self.n_users, w), local_rows(self.n_items, w)
+        lu, li = self.local_users, self.local_items
 
-        def table(name, gname, rows, dim):
+        def table(name, scratch, rows, dim):
             st = self.state[name]
-            return _lib.Table(A.ptr(name), A.ptr(gname), _lib.ptr(st.get("m")), _lib.ptr(st.get("v")), rows, dim, 0)
+            return _lib.Table(A.ptr(name), _lib.ptr(S[scratch]), _lib.ptr(st.get("m")), _lib.ptr(st.get("v")), rows, dim, 0)
 
-        def entity(prefix, rows, cap):
+        def entity(prefix, n_global, rows, cap):
             e = _lib.Entity()
-            e.rows = _lib.Rowset(A.ptr(prefix + "_slot"), A.ptr(prefix + "_list"), A.ptr(prefix + "_count"), rows, cap, 0)
+            e.rows = _lib.Rowset(_lib.ptr(S[prefix + "_slot"]), _lib.ptr(S[prefix + "_list"]),
+                                 _lib.ptr(S[prefix + "_count"]), n_global, cap, 0)  # slot maps over GLOBAL ids
             e.n_tables = 2
-            e.table[0] = table(prefix + "_emb", "g_" + prefix + "_emb", rows, d)
-            e.table[1] = table(prefix + "_bias", "g_" + prefix + "_bias", rows, 1)
+            e.table[0] = table(prefix + "_emb", "s_" + prefix + "_emb", rows, d)
+            e.table[1] = table(prefix + "_bias", "s_" + prefix + "_bias", rows, 1)
             return e
 
         gb = self.state["global_bias"]
-        local = _lib.MfModel(entity("user", lu, self.cap_u), entity("item", li, self.cap_i),
+        stage = _lib.MfModel(entity("user", self.n_users, lu, self.cap_u), entity("item", self.n_items, li, self.cap_i),
                              _lib.DenseParam(_lib.ptr(self.global_bias), None, _lib.ptr(gb.get("m")),
                                              _lib.ptr(gb.get("v")), 1), A.ptr("ws"), _lib.Rowset(), _lib.Rowset())
         peers = (_lib.MfPeerTables * w)()
@@ -272,7 +285,11 @@ class ShardedMFEngine(object):
             for f, _ in _lib.MfPeerTables._fields_:
                 setattr(peers[r], f, A.ptr(f, r))
         self._peers_dev = torch.frombuffer(bytearray(bytes(peers)), dtype=torch.uint8).to(self.device)
-        self._cmodel = _lib.MfSharded(w, self.rank, self.n_users, self.n_items, local, self._peers_dev.data_ptr())
+        own = _lib.MfPeerTables()
+        for f, _ in _lib.MfPeerTables._fields_:
+            setattr(own, f, A.ptr(f))
+        self._cmodel = _lib.MfSharded(w, self.rank, self.n_users, self.n_items, lu, li, stage,
+                                      self._peers_dev.data_ptr(), own)
         self._sync = _lib.PeerSync()
         self._sync.world, self._sync.rank = w, self.rank
         for r in range(w):
@@ -311,9 +328,10 @@ class ShardedMFEngine(object):
         _lib.check(self.lib.brs_mf_sharded_bpr_fwd_bwd(C.byref(self._cmodel), _lib.ptr(users), _lib.ptr(pos),
                                                        _lib.ptr(neg), users.numel(), gb, float(self.reg),
                                                        self._stream()), "brs_mf_sharded_bpr_fwd_bwd")
-        self._barrier(with_sums=True)  # all ranks' peer REDs have landed; step sums exchanged
-        _lib.check(self.lib.brs_mf_apply(C.byref(self._cmodel.local), C.byref(self.opt), gb,
-                                         _lib.ptr(self._out if out is None else out), self._stream()), "brs_mf_apply")
+        self._barrier(with_sums=True)  # all ranks' pushed gradient rows have landed; step sums exchanged
+        _lib.check(self.lib.brs_mf_sharded_apply(C.byref(self._cmodel), C.byref(self.opt), gb,
+                                                 _lib.ptr(self._out if out is None else out), self._stream()),
+                   "brs_mf_sharded_apply")
         self._barrier(with_sums=False)  # every shard updated before anyone gathers again
 
     def train_batches(self, users, pos, neg):

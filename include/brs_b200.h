@@ -132,11 +132,10 @@ typedef struct brs_mf_model {
 /* one rank's MF shard as seen from the calling process (pointers mapped through CUDA IPC / NVLink peer
  * access); a device-resident array of these, indexed by rank, drives the row-sharded kernels */
 typedef struct brs_mf_peer_tables {
-    const float *user_emb, *item_emb, *user_bias, *item_bias;
-    float *g_user_emb, *g_item_emb, *g_user_bias, *g_item_bias;
-    int32_t *user_slot, *item_slot;    /* slot maps   (brs_rowset.slot_map) */
-    int32_t *user_list, *item_list;    /* slot lists  (brs_rowset.list)     */
-    int32_t *user_count, *item_count;  /* slot counts (brs_rowset.count)    */
+    const float *user_emb, *item_emb, *user_bias, *item_bias;    /* shard weights [local_rows, dim] / [local_rows] */
+    float *g_user_emb, *g_item_emb, *g_user_bias, *g_item_bias;  /* DENSE per-shard gradient tables, same shapes,
+                                                                    row-major, all-zero between steps */
+    uint32_t *user_bits, *item_bits;                             /* touched bitmaps [(local_rows+31)/32] */
 } brs_mf_peer_tables;
 
 /* library / device */
@@ -328,9 +327,13 @@ int brs_dense_params_step(const brs_dense_param *params, int32_t n_params, const
 /* ---- multi-GPU: row-sharded tables over NVLink peer memory (new work, the
  *      reference has no distributed path) ----
  * owner(row) = row mod world, local row = row div world (world a power of two <= 8).  Every rank maps
- * every other rank's shard (CUDA IPC) and the kernels address it directly: gathers are peer loads,
- * gradient scatters are peer REDs into the OWNER's compact scratch, slots are claimed with peer atomics.
- * Ranks meet at two flag barriers per step (no NCCL on the data path). */
+ * every other rank's shard (CUDA IPC) and the kernels address it directly:
+ *   - the fused kernel gathers embedding rows with peer loads and accumulates the batch's gradients in a
+ *     LOCAL compact scratch (slots over GLOBAL ids) -- no remote atomics per sample;
+ *   - a push kernel then adds ONE coalesced row per unique touched row into the OWNER's dense per-shard
+ *     gradient table (128-bit peer REDs) and sets the row's bit in the owner's touched bitmap (red.or);
+ *   - after a flag barrier every owner applies the optimizer to the rows whose bit is set.
+ * Two flag barriers per step, no NCCL on the data path. */
 #define BRS_MAX_RANKS 8
 #define BRS_IPC_HANDLE_BYTES 64
 
@@ -357,16 +360,25 @@ int brs_peer_barrier(const brs_peer_sync *sync, uint64_t epoch, void *ws, void *
 typedef struct brs_mf_sharded {
     int32_t world, rank;
     int64_t n_users, n_items;            /* GLOBAL row counts */
-    brs_mf_model local;                  /* this rank's shard (tables hold ceil(N/world) rows) */
-    const brs_mf_peer_tables *peers;     /* DEVICE array [world], peers[rank] = own shard */
+    int64_t local_users, local_items;    /* rows reserved per shard: ceil(N / world) */
+    /* this rank's staging + shard state: rowsets (slot maps) are indexed by GLOBAL ids, table[k].grad is the
+     * local compact scratch; table[k].weight / m / v are this rank's SHARD tables (owner-side optimizer) */
+    brs_mf_model stage;
+    const brs_mf_peer_tables *peers;     /* DEVICE array [world]; peers[rank] = own shard */
+    brs_mf_peer_tables own;              /* host copy of peers[rank] (dense gradients + bitmaps of this shard) */
 } brs_mf_sharded;
 
-/* forward + backward of this rank's `batch` BPR triples (GLOBAL ids) against the sharded tables; the
- * loss is the mean over `global_batch` = sum of all ranks' batches.  Follow with
- * brs_peer_barrier(sync, e, local.ws), brs_mf_apply(&local, opt, global_batch, out), brs_peer_barrier(sync, e+1, NULL). */
+/* forward + backward of this rank's `batch` BPR triples (GLOBAL ids) against the sharded tables, then the
+ * push of the aggregated gradient rows to their owners; the loss is the mean over `global_batch` = sum of
+ * all ranks' batches.  Follow with brs_peer_barrier(sync, e, stage.ws),
+ * brs_mf_sharded_apply(model, opt, global_batch, out), brs_peer_barrier(sync, e+1, NULL). */
 int brs_mf_sharded_bpr_fwd_bwd(const brs_mf_sharded *model, const int64_t *users, const int64_t *pos_items,
                                const int64_t *neg_items, int64_t batch, int64_t global_batch, float reg_weight,
                                void *stream);
+/* optimizer step on this rank's shard for the rows whose touched bit is set (BRS_DENSE Adam/RMSprop: every
+ * row, g = 0 where the bit is clear) + global_bias + publication of {loss, regularizer, status} */
+int brs_mf_sharded_apply(const brs_mf_sharded *model, const brs_opt *opt, int64_t global_batch,
+                         float *out /* brs_step_out */, void *stream);
 
 /* the sharded epoch inner loop over this rank's index arrays resident in HBM (same n and batch on every rank):
  * per batch fwd_bwd, barrier(+sums), apply, barrier; barrier epochs first_epoch, first_epoch+1, ...

@@ -78,8 +78,12 @@ def _worker(rank, world, port, route, optimizer, q):
         assert all(torch.equal(gb[0], x) for x in gb)
         # scratch is clean again on every rank
         for name in ("user_slot", "item_slot"):
-            assert bool((eng.arena.tensor(name) == -1).all().item())
-        assert float(eng.arena.tensor("g_user_emb").abs().max().item()) == 0.0
+            assert bool((eng._stage[name] == -1).all().item())
+        for name in ("g_user_emb", "g_item_emb", "g_user_bias", "g_item_bias"):
+            assert float(eng.arena.tensor(name).abs().max().item()) == 0.0
+        for name in ("user_bits", "item_bits"):
+            assert int(eng.arena.tensor(name).abs().max().item()) == 0
+        assert float(eng._stage["s_user_emb"].abs().max().item()) == 0.0
         eng.close()
         q.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
