@@ -350,14 +350,19 @@ def run_sharded(a, rank, world, local, dev):
             "metric": "BPR interactions/sec", "value": value, "unit": "interactions/s", "n_gpus": world,
             "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": dict(config_dict(a, world), parallelism="row-sharded x%d (owner = row mod N), route=%s" % (world, a.route)),
-            "roofline": {"bound": "nvlink", "kernel": "mf_fwd_bwd_kernel<SHARD> (peer loads + peer REDs)",
+            "config": dict(config_dict(a, world), parallelism="row-sharded x%d (owner = row mod N), route=%s" % (world, a.route),
+                           shard_mode={"1": "direct: per-sample peer gathers in the fused kernel",
+                                       "2": "staged: unique rows pulled once, fused kernel on local staging"}.get(
+                                           os.environ.get("BRS_SHARD_MODE", "1"), "direct")),
+            "roofline": {"bound": "nvlink", "kernel": "mf_fwd_bwd_kernel<SHARD> peer gathers (in) / mf_push_kernel peer REDs (out)",
                          "achieved": nvl_bytes / step_s / 1e9, "peak": 770.0, "unit": "GB/s",
                          "frac": nvl_bytes / step_s / 1e9 / 770.0,
                          "peak_source": "B200_PROFILING.md measured peer copy, per direction per GPU", "traffic": None,
                          "note": "bytes that must cross NVLink per rank per step and direction "
                                  "(remote fraction x batch x 3 rows x 4D, + biases) / whole-step time"},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": 5 * a.steps,
+            "clocks": clocks, "e2e": e2e,
+            # pre-pass, [pull,] fused fwd/bwd, barrier, push, count reset, apply/record, barrier
+            "gpu_launches": (8 if os.environ.get("BRS_SHARD_MODE", "1") == "2" else 7) * a.steps,
             "final_loss": final_loss, "wall_s_timed_region": t_wall1 - t_wall0,
         }
         print(json.dumps(line))

@@ -97,7 +97,8 @@ class PeerSync(C.Structure):
 class MfSharded(C.Structure):
     _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("n_users", C.c_int64), ("n_items", C.c_int64),
                 ("local_users", C.c_int64), ("local_items", C.c_int64), ("stage", MfModel), ("peers", C.c_void_p),
-                ("own", MfPeerTables)]
+                ("own", MfPeerTables), ("pull_user_emb", C.c_void_p), ("pull_item_emb", C.c_void_p),
+                ("pull_user_bias", C.c_void_p), ("pull_item_bias", C.c_void_p)]
 
 
 EXTRA_STRUCTS = {"brs_csr": Csr, "brs_lightgcn_model": LightGCNModel, "brs_ncf_model": NcfModel, "brs_mf_peer_tables": MfPeerTables, "brs_peer_sync": PeerSync,
@@ -149,6 +150,10 @@ _PROTOTYPES = {
     "brs_peer_barrier": (C.c_int, [C.POINTER(PeerSync), C.c_uint64, _P, _P]),
     "brs_mf_sharded_bpr_fwd_bwd": (C.c_int, [C.POINTER(MfSharded), _P, _P, _P, C.c_int64, C.c_int64, C.c_float, _P]),
     "brs_mf_sharded_apply": (C.c_int, [C.POINTER(MfSharded), C.POINTER(Opt), C.c_int64, _P, _P]),
+    "brs_debug_set_shard_mode": (C.c_int, [C.c_int]),
+    "brs_mf_sharded_push": (C.c_int, [C.POINTER(MfSharded), C.POINTER(Opt), _P]),
+    "brs_mf_sharded_step": (C.c_int, [C.POINTER(MfSharded), C.POINTER(PeerSync), C.POINTER(Opt), _P, _P, _P, C.c_int64,
+                                      C.c_int64, C.c_float, C.c_uint64, _P, _P]),
     "brs_mf_sharded_train_batches": (C.c_int, [C.POINTER(MfSharded), C.POINTER(PeerSync), C.POINTER(Opt), _P, _P, _P,
                                                C.c_int64, C.c_int64, C.c_int64, C.c_float, C.c_uint64, _P, _P]),
     "brs_route_triples": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, _P, _P, _P, _P, _P]),

@@ -172,6 +172,32 @@ extern "C" int brs_mf_train_batches(const brs_mf_model* model, const brs_opt* op
 }
 
 // the sharded epoch inner loop: every rank calls it with ITS OWN index arrays (same n / batch on all ranks)
+extern "C" int brs_mf_sharded_step(const brs_mf_sharded* model, const brs_peer_sync* sync, const brs_opt* opt,
+                                  const int64_t* users, const int64_t* pos_items, const int64_t* neg_items,
+                                  int64_t batch, int64_t global_batch, float reg_weight, uint64_t epoch, float* out,
+                                  void* stream) {
+    if (!model || !sync || !opt || !out || epoch == 0) return BRS_ERR_INVALID_ARG;
+    int rc = brs_mf_sharded_bpr_fwd_bwd(model, users, pos_items, neg_items, batch, global_batch, reg_weight, stream);
+    if (rc != BRS_OK) return rc;
+    if (opt->kind == BRS_SGD) {
+        // the push updates the owners' weights in place: every rank must be done gathering first
+        rc = brs_peer_barrier(sync, epoch, model->stage.ws, stream);
+        if (rc != BRS_OK) return rc;
+        rc = brs_mf_sharded_push(model, opt, stream);
+        if (rc != BRS_OK) return rc;
+        rc = brs_mf_sharded_apply(model, opt, global_batch, out, stream);
+        if (rc != BRS_OK) return rc;
+        return brs_peer_barrier(sync, epoch + 1, nullptr, stream);
+    }
+    rc = brs_mf_sharded_push(model, opt, stream);
+    if (rc != BRS_OK) return rc;
+    rc = brs_peer_barrier(sync, epoch, model->stage.ws, stream);
+    if (rc != BRS_OK) return rc;
+    rc = brs_mf_sharded_apply(model, opt, global_batch, out, stream);
+    if (rc != BRS_OK) return rc;
+    return brs_peer_barrier(sync, epoch + 1, nullptr, stream);
+}
+
 extern "C" int brs_mf_sharded_train_batches(const brs_mf_sharded* model, const brs_peer_sync* sync, const brs_opt* opt,
                                             const int64_t* users, const int64_t* pos_items, const int64_t* neg_items,
                                             int64_t n, int64_t batch, int64_t global_batch, float reg_weight,
@@ -180,16 +206,11 @@ extern "C" int brs_mf_sharded_train_batches(const brs_mf_sharded* model, const b
         return BRS_ERR_INVALID_ARG;
     uint64_t epoch = first_epoch;
     int64_t b = 0;
-    for (int64_t off = 0; off < n; off += batch, ++b) {
+    for (int64_t off = 0; off < n; off += batch, ++b, epoch += 2) {
         const int64_t cur = (n - off < batch) ? (n - off) : batch;
         const int64_t gb = (cur == batch) ? global_batch : cur * model->world;
-        int rc = brs_mf_sharded_bpr_fwd_bwd(model, users + off, pos_items + off, neg_items + off, cur, gb, reg_weight, stream);
-        if (rc != BRS_OK) return rc;
-        rc = brs_peer_barrier(sync, epoch++, model->stage.ws, stream);
-        if (rc != BRS_OK) return rc;
-        rc = brs_mf_sharded_apply(model, opt, gb, out + 4 * b, stream);
-        if (rc != BRS_OK) return rc;
-        rc = brs_peer_barrier(sync, epoch++, nullptr, stream);
+        int rc = brs_mf_sharded_step(model, sync, opt, users + off, pos_items + off, neg_items + off, cur, gb, reg_weight,
+                                     epoch, out + 4 * b, stream);
         if (rc != BRS_OK) return rc;
     }
     return BRS_OK;

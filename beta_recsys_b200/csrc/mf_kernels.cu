@@ -36,6 +36,7 @@ constexpr int kWarps = kThreads / 32;
 constexpr int kTile = 32;  // samples per staged index tile (double-buffered)
 
 enum { LOSS_BPR = 0, LOSS_BCE = 1 };
+enum { SHARD_NONE = 0, SHARD_DIRECT = 1, SHARD_STAGED = 2 };
 
 struct MfPeerTables {  // one rank's shard, as seen from this process (device-resident array of these)
     const float* user_emb;
@@ -69,7 +70,8 @@ struct MfArgs {
     const int* __restrict__ item_slot;
     // row-sharded multi-GPU mode (SHARD = true): row r lives on rank r & shard_mask at local row
     // r >> shard_shift; peers[rank] holds that rank's tables as pointers mapped into THIS process
-    // (NVLink peer memory), so gathers are peer loads and gradient scatters are peer REDs
+    // (NVLink peer memory).  The fused kernel itself only sees LOCAL memory: user_emb/item_emb/...
+    // point at this rank's staging tables (one row per slot), filled by mf_pull_kernel
     const MfPeerTables* __restrict__ peers;
     int shard_shift, shard_mask;
     int user_cap, item_cap;  // capacity of the gradient scratch (sector-blocked layout, common.cuh gs_off)
@@ -106,11 +108,10 @@ struct Sample {
     bool valid;
     float4 ue[VPL], ie[VPL], je[VPL];
     float bu, bi, bj;
-    int su, si, sj;  // gradient-scratch slots
-    int ou, oi, oj;  // owning ranks (SHARD only)
+    int su, si, sj;  // gradient-scratch slots (SHARD: also the rows of the staging tables)
 };
 
-template <int LPR, int VPL, bool FULL, int LOSS, bool SHARD>
+template <int LPR, int VPL, bool FULL, int LOSS, int SHARD>
 __device__ __forceinline__ void sample_load(const MfArgs& a, const IdxTile& T, int s, int tile_n, int gl, int D,
                                             unsigned long long pol_g, Sample<VPL, LOSS>& x) {
     x.valid = s < tile_n;
@@ -134,21 +135,33 @@ __device__ __forceinline__ void sample_load(const MfArgs& a, const IdxTile& T, i
     const float *t_ue = a.user_emb, *t_ie = a.item_emb, *t_je = a.item_emb;
     const float *t_ub = a.user_bias, *t_ib = a.item_bias, *t_jb = a.item_bias;
     const int *t_us = a.user_slot, *t_is = a.item_slot, *t_js = a.item_slot;
-    x.ou = x.oi = x.oj = 0;
-    if (SHARD) {
-        x.ou = lu & a.shard_mask;
-        x.oi = li & a.shard_mask;
-        x.oj = lj & a.shard_mask;
+    if (SHARD == SHARD_DIRECT) {
+        // rows are gathered from their owners' shards with peer loads (NVLink), once per sample
+        const int ou = lu & a.shard_mask, oi = li & a.shard_mask, oj = lj & a.shard_mask;
         lu >>= a.shard_shift;
         li >>= a.shard_shift;
         lj >>= a.shard_shift;
-        const MfPeerTables *pu = a.peers + x.ou, *pi = a.peers + x.oi, *pj = a.peers + x.oj;
+        const MfPeerTables *pu = a.peers + ou, *pi = a.peers + oi, *pj = a.peers + oj;
         t_ue = ldg_ptr(&pu->user_emb);
         t_ie = ldg_ptr(&pi->item_emb);
         t_je = ldg_ptr(&pj->item_emb);
         t_ub = ldg_ptr(&pu->user_bias);
         t_ib = ldg_ptr(&pi->item_bias);
         t_jb = ldg_ptr(&pj->item_bias);
+    }
+    if (SHARD == SHARD_STAGED) {
+        // the batch's unique rows were pulled from their owners into THIS rank's compact staging tables
+        // (mf_pull_kernel), one row per slot -- the same slots the gradient scratch uses
+        x.su = __ldg(t_us + lu);
+        x.si = __ldg(t_is + li);
+        x.sj = (LOSS == LOSS_BPR) ? __ldg(t_js + lj) : 0;
+        if (x.su < 0 || x.si < 0 || x.sj < 0) {  // capacity overflow, flagged by the pre-pass
+            x.valid = false;
+            x.su = x.si = x.sj = 0;
+        }
+        lu = (unsigned)x.su;
+        li = (unsigned)x.si;
+        lj = (unsigned)x.sj;
     }
     // rows < 2^31 (slot maps are int32), so one 32x32->64 IMAD.WIDE per row address
     const float* ur = t_ue + (unsigned long long)lu * (unsigned)D;
@@ -165,11 +178,13 @@ __device__ __forceinline__ void sample_load(const MfArgs& a, const IdxTile& T, i
     x.bu = __ldg(t_ub + lu);
     x.bi = __ldg(t_ib + li);
     x.bj = (LOSS == LOSS_BPR) ? __ldg(t_jb + lj) : 0.f;
-    // slots of the LOCAL compact scratch: indexed by the (global) id, assigned by this rank's pre-pass
-    x.su = __ldg(t_us + (unsigned)x.u);
-    x.si = __ldg(t_is + (unsigned)x.i);
-    x.sj = (LOSS == LOSS_BPR) ? __ldg(t_js + (unsigned)x.j) : 0;
-    if (x.su < 0 || x.si < 0 || x.sj < 0) x.valid = false;  // capacity overflow, flagged by the pre-pass
+    if (SHARD != SHARD_STAGED) {
+        // slots of the compact gradient scratch: indexed by the row id, assigned by the pre-pass
+        x.su = __ldg(t_us + (unsigned)x.u);
+        x.si = __ldg(t_is + (unsigned)x.i);
+        x.sj = (LOSS == LOSS_BPR) ? __ldg(t_js + (unsigned)x.j) : 0;
+        if (x.su < 0 || x.si < 0 || x.sj < 0) x.valid = false;  // capacity overflow, flagged by the pre-pass
+    }
 }
 
 // FAST = true evaluates the sigmoid / log chain with the MUFU approximations (__expf, __logf,
@@ -179,7 +194,7 @@ __device__ __forceinline__ float sig_(float x) {
     return FAST ? __fdividef(1.0f, 1.0f + __expf(-x)) : sigmoidf_(x);
 }
 
-template <int LPR, int VPL, bool FULL, int LOSS, bool SHARD, bool FAST>
+template <int LPR, int VPL, bool FULL, int LOSS, int SHARD, bool FAST>
 __device__ __forceinline__ void sample_finish(const MfArgs& a, const Sample<VPL, LOSS>& x, int gl, int D, float bg,
                                               unsigned long long pol_s, float& loss_acc, float& reg_acc,
                                               float& gb_acc) {
@@ -296,7 +311,7 @@ __device__ __forceinline__ bool stage_tile(const MfArgs& a, long long t, IdxTile
     return used_tma;
 }
 
-template <int LPR, int VPL, bool FULL, int LOSS, bool SHARD, int UNROLL, int MINB, bool FAST>
+template <int LPR, int VPL, bool FULL, int LOSS, int SHARD, int UNROLL, int MINB, bool FAST>
 __global__ void __launch_bounds__(kThreads, MINB) mf_fwd_bwd_kernel(const MfArgs a) {
     constexpr int SPW = 32 / LPR;
     __shared__ IdxTile s_tile[2];
@@ -440,7 +455,20 @@ int mf_variant() {
     return g_mf_variant;
 }
 
-template <int LOSS, bool SHARD = false>
+// how the row-sharded step reads remote rows: SHARD_DIRECT gathers them per sample with peer loads inside
+// the fused kernel; SHARD_STAGED pulls each unique row once into local staging tables first.
+// BRS_SHARD_MODE=1|2 or brs_debug_set_shard_mode
+int g_shard_mode = -1;
+int shard_mode() {
+    if (g_shard_mode < 0) {
+        const char* e = getenv("BRS_SHARD_MODE");
+        const int m = e ? atoi(e) : SHARD_DIRECT;
+        g_shard_mode = (m == SHARD_STAGED) ? SHARD_STAGED : SHARD_DIRECT;
+    }
+    return g_shard_mode;
+}
+
+template <int LOSS, int SHARD = SHARD_NONE>
 int launch_fwd_bwd(const MfArgs& a, cudaStream_t st) {
     const int D = a.dim;
     const long long n_tiles = (a.batch + kTile - 1) / kTile;
@@ -451,7 +479,7 @@ int launch_fwd_bwd(const MfArgs& a, cudaStream_t st) {
     } while (0)
 #define BRS_LAUNCH(LPR, VPL, FULL) BRS_LAUNCHX(LPR, VPL, FULL, 1, ((VPL) <= 2 ? 8 : (SHARD ? 4 : 5)), false)
     if (D % 4 != 0 || D <= 0 || D > 512) return BRS_ERR_UNSUPPORTED;
-    if (D == 128 && LOSS == LOSS_BPR && !SHARD && mf_variant() != 0) {
+    if (D == 128 && LOSS == LOSS_BPR && mf_variant() != 0) {
         switch (mf_variant()) {
             case 1: BRS_LAUNCHX(8, 4, true, 1, 6, false); break;
             case 2: BRS_LAUNCHX(16, 2, true, 2, 5, false); break;
@@ -655,20 +683,83 @@ struct PushArgs {
     float* scratch_emb[2];    // local compact scratch (sector-blocked)
     float* scratch_bias[2];
     int dim, shift, mask;
+    float scale;              // DIRECT: -lr
 };
 
 __device__ __forceinline__ void red_or_u32(unsigned int* p, unsigned int v) {
     asm volatile("red.relaxed.sys.global.or.b32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// one warp per touched slot: 128-bit REDs of the whole row into the owner's dense gradient table
-// (coalesced 16*lanes-byte bursts over NVLink), bias, touched bit; the local scratch row is zeroed
-// and the local slot released on the way.
+// one warp per unique row of the batch (slot s of the local rowsets): copy the row and its bias from the
+// owner's shard (peer loads over NVLink, or local) into this rank's staging tables at row s.  Every unique
+// row crosses NVLink ONCE per step however many samples use it; two rows per warp in flight.
+struct PullArgs {
+    const MfPeerTables* __restrict__ peers;
+    brs_rowset rows[2];
+    float* stage_emb[2];   // [capacity, D] row-major
+    float* stage_bias[2];  // [capacity]
+    int dim, shift, mask;
+};
+
+__global__ void __launch_bounds__(256) mf_pull_kernel(const PullArgs a) {
+    constexpr int R = 4;  // rows in flight per warp
+    const int lane = threadIdx.x & 31;
+    const int D = a.dim;
+    const int cu = min(*a.rows[0].count, a.rows[0].capacity), ci = min(*a.rows[1].count, a.rows[1].capacity);
+    const int total = cu + ci;
+    const int n_warps = gridDim.x * 8;
+    for (int w0 = blockIdx.x * 8 + (threadIdx.x >> 5); w0 < total; w0 += R * n_warps) {
+        const float* src[R];
+        float* dst[R];
+        const float* bsrc[R];
+        float* bdst[R];
+        bool on[R];
+        unsigned g[R];
+        int e[R], sl[R];
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            const int w = w0 + k * n_warps;
+            on[k] = w < total;
+            e[k] = (on[k] && w >= cu) ? 1 : 0;
+            sl[k] = on[k] ? (e[k] == 0 ? w : w - cu) : 0;
+            g[k] = (unsigned)a.rows[e[k]].list[sl[k]];
+        }
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            const MfPeerTables* pt = a.peers + (int)(g[k] & (unsigned)a.mask);
+            const unsigned lrow = g[k] >> a.shift;
+            src[k] = (e[k] == 0 ? ldg_ptr(&pt->user_emb) : ldg_ptr(&pt->item_emb)) + (size_t)lrow * (unsigned)D;
+            bsrc[k] = (e[k] == 0 ? ldg_ptr(&pt->user_bias) : ldg_ptr(&pt->item_bias)) + lrow;
+            dst[k] = a.stage_emb[e[k]] + (size_t)sl[k] * (unsigned)D;
+            bdst[k] = a.stage_bias[e[k]] + sl[k];
+        }
+        for (int c = lane * 4; c < D; c += 128) {
+            float4 v[R];
+#pragma unroll
+            for (int k = 0; k < R; ++k)
+                if (on[k]) v[k] = ld_row4(src[k] + c);
+#pragma unroll
+            for (int k = 0; k < R; ++k)
+                if (on[k]) *(float4*)(dst[k] + c) = v[k];
+        }
+#pragma unroll
+        for (int k = 0; k < R; ++k)
+            if (lane == k && on[k]) *bdst[k] = __ldg(bsrc[k]);
+    }
+}
+
+// one warp per touched slot: 128-bit REDs of the whole row to its owner (coalesced 16*lanes-byte bursts
+// over NVLink); the local scratch row is zeroed and the local slot released on the way.
+//   DIRECT (SGD, linear in the gradient): adds -lr * g straight into the owner's WEIGHT row -- no dense
+//           gradient table, no bitmap, no owner-side pass; needs a barrier between the last gather and here.
+//   else  : adds g into the owner's dense per-shard gradient table and sets the row's touched bit.
+template <bool DIRECT>
 __global__ void __launch_bounds__(256) mf_push_kernel(const PushArgs a) {
     const int lane = threadIdx.x & 31;
     const int D = a.dim;
     const int cu = min(*a.rows[0].count, a.rows[0].capacity), ci = min(*a.rows[1].count, a.rows[1].capacity);
     const int total = cu + ci;
+    const float sc = a.scale;
     for (int w = blockIdx.x * 8 + (threadIdx.x >> 5); w < total; w += gridDim.x * 8) {
         const int e = w < cu ? 0 : 1;
         const int s = e == 0 ? w : w - cu;
@@ -677,18 +768,28 @@ __global__ void __launch_bounds__(256) mf_push_kernel(const PushArgs a) {
         const int owner = (int)(g & (unsigned)a.mask);
         const unsigned lrow = g >> a.shift;
         const MfPeerTables* pt = a.peers + owner;
-        float* dst = (e == 0 ? ldg_ptr(&pt->g_user_emb) : ldg_ptr(&pt->g_item_emb)) + (size_t)lrow * (unsigned)D;
+        float* base;
+        if (DIRECT)
+            base = (float*)(e == 0 ? ldg_ptr(&pt->user_emb) : ldg_ptr(&pt->item_emb));
+        else
+            base = e == 0 ? ldg_ptr(&pt->g_user_emb) : ldg_ptr(&pt->g_item_emb);
+        float* dst = base + (size_t)lrow * (unsigned)D;
         for (int c = lane * 4; c < D; c += 128) {
             float* src = a.scratch_emb[e] + gs_off(D, rs.capacity, (unsigned)s, c);
-            const float4 v = *(const float4*)src;
+            float4 v = *(const float4*)src;
+            if (DIRECT) v = make_float4(sc * v.x, sc * v.y, sc * v.z, sc * v.w);
             red_add4(dst + c, v);
             *(float4*)src = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         if (lane == 0) {
             float* sb = a.scratch_bias[e] + s;
-            red_add1((e == 0 ? ldg_ptr(&pt->g_user_bias) : ldg_ptr(&pt->g_item_bias)) + lrow, *sb);
+            if (DIRECT) {
+                red_add1((float*)(e == 0 ? ldg_ptr(&pt->user_bias) : ldg_ptr(&pt->item_bias)) + lrow, sc * *sb);
+            } else {
+                red_add1((e == 0 ? ldg_ptr(&pt->g_user_bias) : ldg_ptr(&pt->g_item_bias)) + lrow, *sb);
+                red_or_u32((e == 0 ? ldg_ptr(&pt->user_bits) : ldg_ptr(&pt->item_bits)) + (lrow >> 5), 1u << (lrow & 31));
+            }
             *sb = 0.f;
-            red_or_u32((e == 0 ? ldg_ptr(&pt->user_bits) : ldg_ptr(&pt->item_bits)) + (lrow >> 5), 1u << (lrow & 31));
             rs.slot_map[g] = BRS_SLOT_NONE;
         }
     }
@@ -737,10 +838,47 @@ extern "C" int brs_mf_sharded_bpr_fwd_bwd(const brs_mf_sharded* model, const int
         rc = brs_assign_slots(rs, idx, n, 3, a.ws, st);
         if (rc != BRS_OK) return rc;
     }
-    rc = launch_fwd_bwd<LOSS_BPR, true>(a, st);
-    if (rc != BRS_OK) return rc;
-    PushArgs p;
+    if (shard_mode() == SHARD_DIRECT) return launch_fwd_bwd<LOSS_BPR, SHARD_DIRECT>(a, st);
+    if (!model->pull_user_emb || !model->pull_item_emb || !model->pull_user_bias || !model->pull_item_bias)
+        return BRS_ERR_INVALID_ARG;
+    PullArgs p;
     p.peers = a.peers;
+    p.rows[0] = model->stage.user.rows;
+    p.rows[1] = model->stage.item.rows;
+    p.stage_emb[0] = model->pull_user_emb;
+    p.stage_emb[1] = model->pull_item_emb;
+    p.stage_bias[0] = model->pull_user_bias;
+    p.stage_bias[1] = model->pull_item_bias;
+    p.dim = a.dim;
+    p.shift = shift;
+    p.mask = w - 1;
+    mf_pull_kernel<<<brs_sm_count() * 8, 256, 0, st>>>(p);
+    // the fused kernel now runs on local memory only: staging rows, indexed by slot
+    a.user_emb = model->pull_user_emb;
+    a.item_emb = model->pull_item_emb;
+    a.user_bias = model->pull_user_bias;
+    a.item_bias = model->pull_item_bias;
+    return launch_fwd_bwd<LOSS_BPR, SHARD_STAGED>(a, st);
+}
+
+extern "C" int brs_debug_set_shard_mode(int mode) {
+    if (mode != SHARD_DIRECT && mode != SHARD_STAGED) return BRS_ERR_INVALID_ARG;
+    g_shard_mode = mode;
+    return BRS_OK;
+}
+
+extern "C" int brs_mf_sharded_push(const brs_mf_sharded* model, const brs_opt* opt, void* stream) {
+    if (!model || !model->peers || !opt) return BRS_ERR_INVALID_ARG;
+    const int w = model->world;
+    if (w < 1 || w > BRS_MAX_RANKS || (w & (w - 1)) != 0) return BRS_ERR_UNSUPPORTED;
+    MfArgs a;
+    int rc = fill_args(&model->stage, a, true);
+    if (rc != BRS_OK) return rc;
+    int shift = 0;
+    while ((1 << shift) < w) ++shift;
+    cudaStream_t st = (cudaStream_t)stream;
+    PushArgs p;
+    p.peers = (const MfPeerTables*)model->peers;
     p.rows[0] = model->stage.user.rows;
     p.rows[1] = model->stage.item.rows;
     p.scratch_emb[0] = a.g_user_emb;
@@ -750,7 +888,11 @@ extern "C" int brs_mf_sharded_bpr_fwd_bwd(const brs_mf_sharded* model, const int
     p.dim = a.dim;
     p.shift = shift;
     p.mask = w - 1;
-    mf_push_kernel<<<brs_sm_count() * 4, 256, 0, st>>>(p);
+    p.scale = -(float)opt->lr;
+    if (opt->kind == BRS_SGD)
+        mf_push_kernel<true><<<brs_sm_count() * 4, 256, 0, st>>>(p);
+    else
+        mf_push_kernel<false><<<brs_sm_count() * 4, 256, 0, st>>>(p);
     mf_push_reset_kernel<<<1, 32, 0, st>>>(model->stage.user.rows.count, model->stage.item.rows.count);
     BRS_CUDA_CHECK(cudaGetLastError());
     return BRS_OK;

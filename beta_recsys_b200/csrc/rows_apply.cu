@@ -492,6 +492,9 @@ struct ShardApplyArgs {
     ApplyArgs base;  // opt, ws, out, inv_batch, global-bias dense param, finalize bookkeeping
 };
 
+// Owner-side optimizer pass over the touched bitmap.  A warp takes one BYTE of the bitmap (8 rows) at a
+// time and keeps up to four rows in flight (all loads issued before the first dependent store), so a
+// dense word -- every item row at large global batches -- costs two load round trips, not 32.
 template <int KIND>
 __global__ void __launch_bounds__(kThreads) shard_apply_kernel(const ShardApplyArgs a) {
     __shared__ OptScalars s_opt;
@@ -500,42 +503,61 @@ __global__ void __launch_bounds__(kThreads) shard_apply_kernel(const ShardApplyA
     const OptScalars s = s_opt;
     const int lane = threadIdx.x & 31;
     const int D = a.dim;
-    const long long words0 = (a.ent[0].rows + 31) >> 5, words1 = (a.ent[1].rows + 31) >> 5;
-    // a warp per bitmap word (32 rows)
-    for (long long wi = (long long)blockIdx.x * kWarps + (threadIdx.x >> 5); wi < words0 + words1;
-         wi += (long long)gridDim.x * kWarps) {
-        const ShardEnt& e = a.ent[wi < words0 ? 0 : 1];
-        const long long word = wi < words0 ? wi : wi - words0;
-        const unsigned int bits = e.bits[word];
+    constexpr int R = 4;
+    const long long tasks0 = (a.ent[0].rows + 7) >> 3, tasks1 = (a.ent[1].rows + 7) >> 3;
+    for (long long ti = (long long)blockIdx.x * kWarps + (threadIdx.x >> 5); ti < tasks0 + tasks1;
+         ti += (long long)gridDim.x * kWarps) {
+        const ShardEnt& e = a.ent[ti < tasks0 ? 0 : 1];
+        const long long task = ti < tasks0 ? ti : ti - tasks0;
+        unsigned char* bytes = (unsigned char*)e.bits;  // little-endian: byte k of the bitmap = rows 8k..8k+7
+        const unsigned int bits = bytes[task];
         unsigned int todo = bits;
         if (a.dense_all) {
-            const long long left = e.rows - word * 32;
-            todo = left >= 32 ? 0xffffffffu : ((1u << left) - 1u);
+            const long long left = e.rows - task * 8;
+            todo = left >= 8 ? 0xffu : ((1u << left) - 1u);
         }
+        const long long row0 = task * 8;
         while (todo) {
-            const int b = __ffs(todo) - 1;
-            todo &= todo - 1;
-            const bool touched = (bits >> b) & 1u;
-            const long long row = word * 32 + b;
-            for (int c = lane * 4; c < D; c += 128) {
-                const size_t o = (size_t)row * D + c;
-                float4 gv = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (touched) {
-                    gv = *(const float4*)(e.g + o);
-                    *(float4*)(e.g + o) = make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-                float4 wv = *(const float4*)(e.w + o);
-                float4 mv = make_float4(0.f, 0.f, 0.f, 0.f), vv = mv;
-                if (KIND == BRS_ADAM) mv = *(const float4*)(e.m + o);
-                if (KIND != BRS_SGD) vv = *(const float4*)(e.v + o);
-                opt_elem4<KIND>(wv, gv, mv, vv, s);
-                *(float4*)(e.w + o) = wv;
-                if (KIND == BRS_ADAM) *(float4*)(e.m + o) = mv;
-                if (KIND != BRS_SGD) *(float4*)(e.v + o) = vv;
+            int rb[R];
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+                rb[k] = todo ? __ffs(todo) - 1 : -1;
+                todo &= todo - 1;  // 0 stays 0
             }
-            if (lane == 0) {
+            for (int c = lane * 4; c < D; c += 128) {
+                float4 gv[R], wv[R], mv[R], vv[R];
+#pragma unroll
+                for (int k = 0; k < R; ++k) {
+                    gv[k] = mv[k] = vv[k] = wv[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (rb[k] >= 0) {
+                        const size_t o = (size_t)(row0 + rb[k]) * D + c;
+                        if ((bits >> rb[k]) & 1u) gv[k] = *(const float4*)(e.g + o);
+                        wv[k] = *(const float4*)(e.w + o);
+                        if (KIND == BRS_ADAM) mv[k] = *(const float4*)(e.m + o);
+                        if (KIND != BRS_SGD) vv[k] = *(const float4*)(e.v + o);
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < R; ++k) {
+                    if (rb[k] >= 0) {
+                        const size_t o = (size_t)(row0 + rb[k]) * D + c;
+                        opt_elem4<KIND>(wv[k], gv[k], mv[k], vv[k], s);
+                        *(float4*)(e.w + o) = wv[k];
+                        if (KIND == BRS_ADAM) *(float4*)(e.m + o) = mv[k];
+                        if (KIND != BRS_SGD) *(float4*)(e.v + o) = vv[k];
+                        if ((bits >> rb[k]) & 1u) *(float4*)(e.g + o) = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
+            }
+            // biases: lane k owns row rb[k]
+            int my = -1;
+#pragma unroll
+            for (int k = 0; k < R; ++k)
+                if (lane == k) my = rb[k];
+            if (my >= 0) {
+                const long long row = row0 + my;
                 float g = 0.f;
-                if (touched) {
+                if ((bits >> my) & 1u) {
                     g = e.gb[row];
                     e.gb[row] = 0.f;
                 }
@@ -548,7 +570,7 @@ __global__ void __launch_bounds__(kThreads) shard_apply_kernel(const ShardApplyA
                 if (KIND != BRS_SGD) e.vb[row] = v;
             }
         }
-        if (lane == 0 && bits) e.bits[word] = 0u;
+        if (lane == 0 && bits) bytes[task] = 0;
     }
     if (last_block(a.base)) finalize<KIND>(a.base, s);
 }
@@ -837,12 +859,16 @@ extern "C" int brs_mf_sharded_apply(const brs_mf_sharded* model, const brs_opt* 
     a.base.inv_batch = 1.0 / (double)global_batch;
     a.base.advance_step = 1;
     cudaStream_t st = (cudaStream_t)stream;
-    const long long words = ((rows[0] + 31) >> 5) + ((rows[1] + 31) >> 5);
+    if (opt->kind == BRS_SGD) {  // brs_mf_sharded_push already applied -lr * g at the owners: only the
+        a.ent[0].rows = 0;       // replicated global bias and the step record are left
+        a.ent[1].rows = 0;
+    }
+    const long long tasks = ((a.ent[0].rows + 7) >> 3) + ((a.ent[1].rows + 7) >> 3);
 #define BRS_SHARD_APPLY(KIND)                                                         \
     do {                                                                              \
         auto k = shard_apply_kernel<KIND>;                                            \
         long long grid = persistent_grid((const void*)k);                             \
-        const long long need = (words + kWarps - 1) / kWarps;                         \
+        const long long need = (tasks + kWarps - 1) / kWarps;                         \
         if (grid > need) grid = need;                                                 \
         k<<<(int)(grid < 1 ? 1 : grid), kThreads, 0, st>>>(a);                        \
     } while (0)

@@ -216,6 +216,11 @@ class ShardedMFEngine(object):
             "user_list": torch.zeros(self.cap_u, dtype=i32, device=dev),
             "item_list": torch.zeros(self.cap_i, dtype=i32, device=dev),
             "user_count": torch.zeros(1, dtype=i32, device=dev), "item_count": torch.zeros(1, dtype=i32, device=dev),
+            # staging tables of the pulled unique rows (one row per slot)
+            "p_user_emb": torch.zeros(self.cap_u * d, dtype=f32, device=dev),
+            "p_item_emb": torch.zeros(self.cap_i * d, dtype=f32, device=dev),
+            "p_user_bias": torch.zeros(self.cap_u, dtype=f32, device=dev),
+            "p_item_bias": torch.zeros(self.cap_i, dtype=f32, device=dev),
             "s_user_emb": torch.zeros(self.cap_u * d, dtype=f32, device=dev),
             "s_item_emb": torch.zeros(self.cap_i * d, dtype=f32, device=dev),
             "s_user_bias": torch.zeros(self.cap_u, dtype=f32, device=dev),
@@ -289,7 +294,8 @@ class ShardedMFEngine(object):
         for f, _ in _lib.MfPeerTables._fields_:
             setattr(own, f, A.ptr(f))
         self._cmodel = _lib.MfSharded(w, self.rank, self.n_users, self.n_items, lu, li, stage,
-                                      self._peers_dev.data_ptr(), own)
+                                      self._peers_dev.data_ptr(), own, _lib.ptr(S["p_user_emb"]),
+                                      _lib.ptr(S["p_item_emb"]), _lib.ptr(S["p_user_bias"]), _lib.ptr(S["p_item_bias"]))
         self._sync = _lib.PeerSync()
         self._sync.world, self._sync.rank = w, self.rank
         for r in range(w):
@@ -325,14 +331,11 @@ class ShardedMFEngine(object):
         gb = int(global_batch) if global_batch is not None else users.numel() * self.world
         if self.route == "owner":
             users, pos, neg = self.route_triples(users, pos, neg)
-        _lib.check(self.lib.brs_mf_sharded_bpr_fwd_bwd(C.byref(self._cmodel), _lib.ptr(users), _lib.ptr(pos),
-                                                       _lib.ptr(neg), users.numel(), gb, float(self.reg),
-                                                       self._stream()), "brs_mf_sharded_bpr_fwd_bwd")
-        self._barrier(with_sums=True)  # all ranks' pushed gradient rows have landed; step sums exchanged
-        _lib.check(self.lib.brs_mf_sharded_apply(C.byref(self._cmodel), C.byref(self.opt), gb,
-                                                 _lib.ptr(self._out if out is None else out), self._stream()),
-                   "brs_mf_sharded_apply")
-        self._barrier(with_sums=False)  # every shard updated before anyone gathers again
+        _lib.check(self.lib.brs_mf_sharded_step(
+            C.byref(self._cmodel), C.byref(self._sync), C.byref(self.opt), _lib.ptr(users), _lib.ptr(pos), _lib.ptr(neg),
+            users.numel(), gb, float(self.reg), self._epoch + 1, _lib.ptr(self._out if out is None else out),
+            self._stream()), "brs_mf_sharded_step")
+        self._epoch += 2
 
     def train_batches(self, users, pos, neg):
         """Many consecutive steps over this rank's index arrays (route='none'): one C call, five

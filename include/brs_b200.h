@@ -328,11 +328,13 @@ int brs_dense_params_step(const brs_dense_param *params, int32_t n_params, const
  *      reference has no distributed path) ----
  * owner(row) = row mod world, local row = row div world (world a power of two <= 8).  Every rank maps
  * every other rank's shard (CUDA IPC) and the kernels address it directly:
- *   - the fused kernel gathers embedding rows with peer loads and accumulates the batch's gradients in a
- *     LOCAL compact scratch (slots over GLOBAL ids) -- no remote atomics per sample;
- *   - a push kernel then adds ONE coalesced row per unique touched row into the OWNER's dense per-shard
- *     gradient table (128-bit peer REDs) and sets the row's bit in the owner's touched bitmap (red.or);
- *   - after a flag barrier every owner applies the optimizer to the rows whose bit is set.
+ *   - the fused kernel gathers embedding rows with peer loads (or, mode 2, from local staging tables that a
+ *     pull kernel filled with every UNIQUE row of the batch once) and accumulates the batch's gradients
+ *     in a LOCAL compact scratch (slots over GLOBAL ids) -- no remote atomics per sample;
+ *   - a push kernel then sends ONE coalesced row per unique touched row to its OWNER with 128-bit peer REDs:
+ *     SGD adds -lr*g into the owner's weights directly; Adam/RMSprop add g into the owner's dense per-shard
+ *     gradient table and set the row's bit in the owner's touched bitmap (red.or), and after a flag barrier
+ *     every owner applies the optimizer to the rows whose bit is set.
  * Two flag barriers per step, no NCCL on the data path. */
 #define BRS_MAX_RANKS 8
 #define BRS_IPC_HANDLE_BYTES 64
@@ -366,23 +368,44 @@ typedef struct brs_mf_sharded {
     brs_mf_model stage;
     const brs_mf_peer_tables *peers;     /* DEVICE array [world]; peers[rank] = own shard */
     brs_mf_peer_tables own;              /* host copy of peers[rank] (dense gradients + bitmaps of this shard) */
+    /* staging tables for the batch's unique rows, one row per slot of stage.{user,item}.rows
+     * ([capacity, dim] row-major / [capacity]); filled by the pull kernel each step */
+    float *pull_user_emb, *pull_item_emb, *pull_user_bias, *pull_item_bias;
 } brs_mf_sharded;
 
-/* forward + backward of this rank's `batch` BPR triples (GLOBAL ids) against the sharded tables, then the
- * push of the aggregated gradient rows to their owners; the loss is the mean over `global_batch` = sum of
- * all ranks' batches.  Follow with brs_peer_barrier(sync, e, stage.ws),
- * brs_mf_sharded_apply(model, opt, global_batch, out), brs_peer_barrier(sync, e+1, NULL). */
+/* forward + backward of this rank's `batch` BPR triples (GLOBAL ids) against the sharded tables: the
+ * pre-pass gives every unique row a slot; rows are read either per sample with peer loads inside the fused
+ * kernel, or (mode 2) a pull kernel copies each unique row ONCE from its owner into the staging tables and
+ * the fused kernel runs on those; the batch's gradients are aggregated in the LOCAL compact scratch; the loss is the mean over `global_batch` = sum of all ranks'
+ * batches. */
 int brs_mf_sharded_bpr_fwd_bwd(const brs_mf_sharded *model, const int64_t *users, const int64_t *pos_items,
                                const int64_t *neg_items, int64_t batch, int64_t global_batch, float reg_weight,
                                void *stream);
-/* optimizer step on this rank's shard for the rows whose touched bit is set (BRS_DENSE Adam/RMSprop: every
- * row, g = 0 where the bit is clear) + global_bias + publication of {loss, regularizer, status} */
+/* how brs_mf_sharded_bpr_fwd_bwd reads remote rows: 1 = per-sample peer loads inside the fused kernel
+ * (default), 2 = pull every unique row once into the staging tables, then compute locally.  Also
+ * BRS_SHARD_MODE in the environment. */
+int brs_debug_set_shard_mode(int mode);
+/* push ONE coalesced row per unique touched row to its owner (128-bit peer REDs) and release the local slots.
+ *   opt->kind == BRS_SGD: adds -lr * g straight into the owner's weight rows (the update is linear in g, so
+ *     no owner-side pass is needed) -- every rank must have finished gathering: barrier BEFORE this call;
+ *   otherwise: adds g into the owner's dense per-shard gradient table and sets the touched bit -- barrier
+ *     AFTER this call, then brs_mf_sharded_apply. */
+int brs_mf_sharded_push(const brs_mf_sharded *model, const brs_opt *opt, void *stream);
+/* owner side: Adam / RMSprop on this rank's shard for the rows whose touched bit is set (BRS_DENSE: every
+ * row, g = 0 where the bit is clear); for every optimizer the replicated global_bias step and the
+ * publication of {loss, regularizer, status}.  Needs the step sums exchanged (brs_peer_barrier with ws). */
 int brs_mf_sharded_apply(const brs_mf_sharded *model, const brs_opt *opt, int64_t global_batch,
                          float *out /* brs_step_out */, void *stream);
+/* one whole step in the right order for opt->kind, with two flag barriers (epochs `epoch`, `epoch`+1):
+ *   SGD : fwd_bwd, barrier(+sums), push (in-place), apply (bias/record), barrier
+ *   else: fwd_bwd, push, barrier(+sums), apply, barrier */
+int brs_mf_sharded_step(const brs_mf_sharded *model, const brs_peer_sync *sync, const brs_opt *opt,
+                        const int64_t *users, const int64_t *pos_items, const int64_t *neg_items, int64_t batch,
+                        int64_t global_batch, float reg_weight, uint64_t epoch, float *out /* brs_step_out */,
+                        void *stream);
 
 /* the sharded epoch inner loop over this rank's index arrays resident in HBM (same n and batch on every rank):
- * per batch fwd_bwd, barrier(+sums), apply, barrier; barrier epochs first_epoch, first_epoch+1, ...
- * (2 per batch); out = brs_step_out[ceil(n/batch)] */
+ * brs_mf_sharded_step per batch; barrier epochs first_epoch, first_epoch+1, ... (2 per batch); out = brs_step_out[ceil(n/batch)] */
 int brs_mf_sharded_train_batches(const brs_mf_sharded *model, const brs_peer_sync *sync, const brs_opt *opt,
                                  const int64_t *users, const int64_t *pos_items, const int64_t *neg_items, int64_t n,
                                  int64_t batch, int64_t global_batch, float reg_weight, uint64_t first_epoch,

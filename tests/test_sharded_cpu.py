@@ -4,6 +4,7 @@ is replaced here by the oracle's stable bucketing -- same contract, checked bit-
 against the kernel in tests/test_sharded_gpu.py)."""
 import os
 import socket
+import sys
 
 import numpy as np
 import pytest
@@ -79,15 +80,26 @@ def _route_worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.timeout(120)
+@pytest.mark.timeout(400)
 def test_triple_routing_exchange_gloo_world2():
     world, port = 2, _free_port()
+    # spawned children unpickle the worker by module name: make sure they can import `tests.*` whatever
+    # earlier tests did to sys.path / the working directory
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    os.environ["PYTHONPATH"] = root + os.pathsep + os.environ.get("PYTHONPATH", "")
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     procs = [ctx.Process(target=_route_worker, args=(r, world, port, q)) for r in range(world)]
-    for p in procs:
-        p.start()
-    res = [q.get(timeout=100) for _ in range(world)]
+    # children re-import this module by name from the parent's sys.path: keep the repo root first (an
+    # earlier test may have put the reference checkout, which has its own `tests` package, in front)
+    saved = sys.path[:]
+    sys.path[:] = [root] + [x for x in saved if x != root]
+    try:
+        for p in procs:
+            p.start()
+    finally:
+        sys.path[:] = saved
+    res = [q.get(timeout=300) for _ in range(world)]
     for p in procs:
         p.join(timeout=30)
     assert sorted(res) == [(0, "ok"), (1, "ok")], res

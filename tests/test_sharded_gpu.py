@@ -4,6 +4,7 @@ GPUs (skipped otherwise).  Parity target: the sharded engines, each fed its own 
 equal the oracle run on the concatenated global batch."""
 import os
 import socket
+import sys
 
 import numpy as np
 import pytest
@@ -40,14 +41,16 @@ def _zipf(rng, n, size, a=1.05):
     return rng.permutation(n)[rng.choice(n, size=size, p=p)].astype(np.int64)
 
 
-def _worker(rank, world, port, route, optimizer, q):
+def _worker(rank, world, port, route, optimizer, q, mode=1):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
+        from beta_recsys_b200 import _lib
         from beta_recsys_b200.sharded import ShardedMFEngine
 
+        _lib.check(_lib.load().brs_debug_set_shard_mode(mode))  # 1: per-sample peer gathers, 2: pull + staging
         nu, ni, d, bsz, lr, steps = 5003, 1999, 128, 1024, 0.05, 3
         rng = np.random.default_rng(7)  # same on every rank: the global model and all batches
         p = _state(rng, nu, ni, d)
@@ -94,15 +97,24 @@ def _worker(rank, world, port, route, optimizer, q):
         dist.destroy_process_group()
 
 
-def _run(world, route, optimizer):
+def _run(world, route, optimizer, mode=1):
     if torch.cuda.device_count() < world:
         pytest.skip("needs %d GPUs" % world)
     port = _free_port()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    os.environ["PYTHONPATH"] = root + os.pathsep + os.environ.get("PYTHONPATH", "")  # children import tests.*
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, route, optimizer, q)) for r in range(world)]
-    for p in procs:
-        p.start()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, route, optimizer, q, mode)) for r in range(world)]
+    # children re-import this module by name from the parent's sys.path: keep the repo root first (an
+    # earlier test may have put the reference checkout, which has its own `tests` package, in front)
+    saved = sys.path[:]
+    sys.path[:] = [root] + [x for x in saved if x != root]
+    try:
+        for p in procs:
+            p.start()
+    finally:
+        sys.path[:] = saved
     res = [q.get(timeout=240) for _ in range(world)]
     for p in procs:
         p.join(timeout=60)
@@ -124,6 +136,13 @@ def test_sharded_world2_matches_oracle_on_the_global_batch(route):
 @pytest.mark.timeout(300)
 def test_sharded_world2_adam_first_step():
     _run(2, "none", "adam")
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("world,optimizer", [(1, "adam"), (2, "sgd"), (2, "adam")])
+def test_sharded_staged_mode_matches_oracle(world, optimizer):
+    """mode 2: every unique row pulled once into the staging tables, fused kernel on local memory"""
+    _run(world, "none", optimizer, mode=2)
 
 
 @pytest.mark.timeout(600)
