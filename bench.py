@@ -353,7 +353,7 @@ def run_sharded(a, rank, world, local, dev):
             "config": dict(config_dict(a, world), parallelism="row-sharded x%d (owner = row mod N), route=%s" % (world, a.route),
                            shard_mode={"1": "direct: per-sample peer gathers in the fused kernel",
                                        "2": "staged: unique rows pulled once, fused kernel on local staging"}.get(
-                                           os.environ.get("BRS_SHARD_MODE", "1"), "direct")),
+                                           os.environ.get("BRS_SHARD_MODE", "2" if world >= 8 else "1"), "direct")),
             "roofline": {"bound": "nvlink", "kernel": "mf_fwd_bwd_kernel<SHARD> peer gathers (in) / mf_push_kernel peer REDs (out)",
                          "achieved": nvl_bytes / step_s / 1e9, "peak": 770.0, "unit": "GB/s",
                          "frac": nvl_bytes / step_s / 1e9 / 770.0,
@@ -362,7 +362,7 @@ def run_sharded(a, rank, world, local, dev):
                                  "(remote fraction x batch x 3 rows x 4D, + biases) / whole-step time"},
             "clocks": clocks, "e2e": e2e,
             # pre-pass, [pull,] fused fwd/bwd, barrier, push, count reset, apply/record, barrier
-            "gpu_launches": (8 if os.environ.get("BRS_SHARD_MODE", "1") == "2" else 7) * a.steps,
+            "gpu_launches": (8 if os.environ.get("BRS_SHARD_MODE", "2" if world >= 8 else "1") == "2" else 7) * a.steps,
             "final_loss": final_loss, "wall_s_timed_region": t_wall1 - t_wall0,
         }
         print(json.dumps(line))

@@ -458,14 +458,17 @@ int mf_variant() {
 // how the row-sharded step reads remote rows: SHARD_DIRECT gathers them per sample with peer loads inside
 // the fused kernel; SHARD_STAGED pulls each unique row once into local staging tables first.
 // BRS_SHARD_MODE=1|2 or brs_debug_set_shard_mode
-int g_shard_mode = -1;
-int shard_mode() {
-    if (g_shard_mode < 0) {
+// Measured (profiles/r01_multigpu.md): direct wins while at most half of the rows are remote
+// (N=2: 773 vs 640 M/s), staged wins once 7/8 of them are (N=8: 2.01 vs 1.96 G/s).
+int g_shard_mode = 0;  // 0: by world size
+int shard_mode(int world) {
+    if (g_shard_mode == 0) {
         const char* e = getenv("BRS_SHARD_MODE");
-        const int m = e ? atoi(e) : SHARD_DIRECT;
-        g_shard_mode = (m == SHARD_STAGED) ? SHARD_STAGED : SHARD_DIRECT;
+        const int m = e ? atoi(e) : 0;
+        g_shard_mode = (m == SHARD_STAGED || m == SHARD_DIRECT) ? m : -1;
     }
-    return g_shard_mode;
+    if (g_shard_mode > 0) return g_shard_mode;
+    return world >= 8 ? SHARD_STAGED : SHARD_DIRECT;
 }
 
 template <int LOSS, int SHARD = SHARD_NONE>
@@ -838,7 +841,7 @@ extern "C" int brs_mf_sharded_bpr_fwd_bwd(const brs_mf_sharded* model, const int
         rc = brs_assign_slots(rs, idx, n, 3, a.ws, st);
         if (rc != BRS_OK) return rc;
     }
-    if (shard_mode() == SHARD_DIRECT) return launch_fwd_bwd<LOSS_BPR, SHARD_DIRECT>(a, st);
+    if (shard_mode(w) == SHARD_DIRECT) return launch_fwd_bwd<LOSS_BPR, SHARD_DIRECT>(a, st);
     if (!model->pull_user_emb || !model->pull_item_emb || !model->pull_user_bias || !model->pull_item_bias)
         return BRS_ERR_INVALID_ARG;
     PullArgs p;
@@ -862,8 +865,8 @@ extern "C" int brs_mf_sharded_bpr_fwd_bwd(const brs_mf_sharded* model, const int
 }
 
 extern "C" int brs_debug_set_shard_mode(int mode) {
-    if (mode != SHARD_DIRECT && mode != SHARD_STAGED) return BRS_ERR_INVALID_ARG;
-    g_shard_mode = mode;
+    if (mode != 0 && mode != SHARD_DIRECT && mode != SHARD_STAGED) return BRS_ERR_INVALID_ARG;
+    g_shard_mode = mode == 0 ? -1 : mode;  // 0: pick by world size
     return BRS_OK;
 }
 

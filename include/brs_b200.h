@@ -381,9 +381,9 @@ typedef struct brs_mf_sharded {
 int brs_mf_sharded_bpr_fwd_bwd(const brs_mf_sharded *model, const int64_t *users, const int64_t *pos_items,
                                const int64_t *neg_items, int64_t batch, int64_t global_batch, float reg_weight,
                                void *stream);
-/* how brs_mf_sharded_bpr_fwd_bwd reads remote rows: 1 = per-sample peer loads inside the fused kernel
- * (default), 2 = pull every unique row once into the staging tables, then compute locally.  Also
- * BRS_SHARD_MODE in the environment. */
+/* how brs_mf_sharded_bpr_fwd_bwd reads remote rows: 1 = per-sample peer loads inside the fused kernel,
+ * 2 = pull every unique row once into the staging tables, then compute locally, 0 = by world size
+ * (default: 2 from 8 ranks up, else 1).  Also BRS_SHARD_MODE in the environment. */
 int brs_debug_set_shard_mode(int mode);
 /* push ONE coalesced row per unique touched row to its owner (128-bit peer REDs) and release the local slots.
  *   opt->kind == BRS_SGD: adds -lr * g straight into the owner's weight rows (the update is linear in g, so

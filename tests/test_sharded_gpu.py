@@ -41,7 +41,7 @@ def _zipf(rng, n, size, a=1.05):
     return rng.permutation(n)[rng.choice(n, size=size, p=p)].astype(np.int64)
 
 
-def _worker(rank, world, port, route, optimizer, q, mode=1):
+def _worker(rank, world, port, route, optimizer, q, mode=0):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
@@ -50,7 +50,7 @@ def _worker(rank, world, port, route, optimizer, q, mode=1):
         from beta_recsys_b200 import _lib
         from beta_recsys_b200.sharded import ShardedMFEngine
 
-        _lib.check(_lib.load().brs_debug_set_shard_mode(mode))  # 1: per-sample peer gathers, 2: pull + staging
+        _lib.check(_lib.load().brs_debug_set_shard_mode(mode))  # 0: by world size, 1: per-sample peer gathers, 2: pull + staging
         nu, ni, d, bsz, lr, steps = 5003, 1999, 128, 1024, 0.05, 3
         rng = np.random.default_rng(7)  # same on every rank: the global model and all batches
         p = _state(rng, nu, ni, d)
@@ -97,7 +97,7 @@ def _worker(rank, world, port, route, optimizer, q, mode=1):
         dist.destroy_process_group()
 
 
-def _run(world, route, optimizer, mode=1):
+def _run(world, route, optimizer, mode=0):
     if torch.cuda.device_count() < world:
         pytest.skip("needs %d GPUs" % world)
     port = _free_port()
