@@ -121,6 +121,8 @@ _PROTOTYPES = {
     "brs_mf_apply": (C.c_int, [C.POINTER(MfModel), C.POINTER(Opt), C.c_int64, _P, _P]),
     "brs_mf_train_batches": (C.c_int, [C.POINTER(MfModel), C.POINTER(Opt), C.c_int32, _P, _P, _P, C.c_int64,
                                        C.c_int64, C.c_float, _P, _P]),
+    "brs_mf_train_batches_host": (C.c_int, [C.POINTER(MfModel), C.POINTER(Opt), C.c_int32, _P, _P, _P, C.c_int64,
+                                       C.c_int64, C.c_float, _P, _P]),
     "brs_mf_predict": (C.c_int, [C.POINTER(MfModel), _P, _P, C.c_int64, _P, _P]),
     "brs_ncf_fwd_bwd": (C.c_int, [C.POINTER(NcfModel), _P, _P, _P, C.c_int64, _P]),
     "brs_ncf_apply": (C.c_int, [C.POINTER(NcfModel), C.POINTER(Opt), C.c_int64, _P, _P]),

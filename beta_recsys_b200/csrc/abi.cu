@@ -113,24 +113,46 @@ extern "C" int brs_mf_apply(const brs_mf_model* model, const brs_opt* opt, int64
                           batch, hint, stream);
 }
 
-extern "C" int brs_mf_train_batches(const brs_mf_model* model, const brs_opt* opt, int32_t loss_kind,
-                                    const int64_t* users, const int64_t* items, const void* third, int64_t n,
-                                    int64_t batch, float reg_weight, float* out_loss_reg, void* stream) {
-    if (!model || !opt || !users || !items || !third || n < 0 || batch <= 0 || !out_loss_reg) return BRS_ERR_INVALID_ARG;
-    const size_t third_sz = loss_kind == 0 ? 8 : 4;
-    // With alternate rowsets and a touched-rows optimizer the slot pre-pass of batch b+1 runs inside the
-    // apply launch of batch b (2 launches per step instead of 3); otherwise the plain 3-launch sequence.
+namespace {
+// where the epoch loop finds batch b's index arrays on the device, and what has to happen around it
+struct BatchFeed {
+    virtual ~BatchFeed() {}
+    virtual void ptrs(int64_t b, const int64_t** users, const int64_t** items, const void** third) = 0;
+    virtual int before_read(int64_t b, cudaStream_t st) { return BRS_OK; }  // batch b is about to be read on st
+    virtual int after_step(int64_t b, float* d_rec, cudaStream_t st) { return BRS_OK; }  // step b fully enqueued
+};
+
+struct ResidentFeed : BatchFeed {  // the whole epoch's arrays already live in HBM
+    const int64_t *users, *items;
+    const char* third;
+    int64_t batch;
+    size_t third_sz;
+    void ptrs(int64_t b, const int64_t** u, const int64_t** i, const void** t) override {
+        *u = users + b * batch;
+        *i = items + b * batch;
+        *t = third + (size_t)(b * batch) * third_sz;
+    }
+};
+
+// Per batch: fused fwd/bwd + apply, 2 launches when the slot pre-pass of batch b+1 can ride in the apply
+// launch of batch b (alternate rowsets + touched-rows optimizer), else the plain 3-launch sequence.
+int mf_epoch_loop(const brs_mf_model* model, const brs_opt* opt, int loss_kind, BatchFeed& feed, int64_t n, int64_t batch,
+                  float reg_weight, float* d_out, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t nb = (n + batch - 1) / batch;
+    auto size_of = [&](int64_t b) { return (b == nb - 1) ? (n - b * batch) : batch; };
     const bool overlap = model->user_rows_alt.slot_map && model->item_rows_alt.slot_map &&
                          (opt->kind == BRS_SGD || opt->mode == BRS_TOUCHED_ROWS);
+    const int64_t *u, *i;
+    const void* t;
+    int rc;
     if (!overlap) {
-        int64_t b = 0;
-        for (int64_t off = 0; off < n; off += batch, ++b) {
-            const int64_t cur = (n - off < batch) ? (n - off) : batch;
-            int rc = brs_mf_fwd_bwd_impl(model, loss_kind, users + off, items + off, (const char*)third + off * third_sz,
-                                         cur, reg_weight, stream);
-            if (rc != BRS_OK) return rc;
-            rc = brs_mf_apply(model, opt, cur, out_loss_reg + 4 * b, stream);
-            if (rc != BRS_OK) return rc;
+        for (int64_t b = 0; b < nb; ++b) {
+            if ((rc = feed.before_read(b, st)) != BRS_OK) return rc;
+            feed.ptrs(b, &u, &i, &t);
+            if ((rc = brs_mf_fwd_bwd_impl(model, loss_kind, u, i, t, size_of(b), reg_weight, stream)) != BRS_OK) return rc;
+            if ((rc = brs_mf_apply(model, opt, size_of(b), d_out + 4 * b, stream)) != BRS_OK) return rc;
+            if ((rc = feed.after_step(b, d_out + 4 * b, st)) != BRS_OK) return rc;
         }
         return BRS_OK;
     }
@@ -139,35 +161,168 @@ extern "C" int brs_mf_train_batches(const brs_mf_model* model, const brs_opt* op
     m[1].item.rows = model->item_rows_alt;
     m[1].user_rows_alt = model->user.rows;
     m[1].item_rows_alt = model->item.rows;
-    if (n > 0) {  // pre-pass of batch 0 on its own
-        const int64_t cur = n < batch ? n : batch;
-        int rc = brs_mf_fwd_bwd_phases(&m[0], loss_kind, users, items, third, cur, reg_weight, stream, 1);
-        if (rc != BRS_OK) return rc;
+    if (nb > 0) {  // pre-pass of batch 0 on its own
+        if ((rc = feed.before_read(0, st)) != BRS_OK) return rc;
+        feed.ptrs(0, &u, &i, &t);
+        if ((rc = brs_mf_fwd_bwd_phases(&m[0], loss_kind, u, i, t, size_of(0), reg_weight, stream, 1)) != BRS_OK) return rc;
     }
-    int64_t b = 0;
-    for (int64_t off = 0; off < n; off += batch, ++b) {
-        const int64_t cur = (n - off < batch) ? (n - off) : batch;
+    for (int64_t b = 0; b < nb; ++b) {
+        const int64_t cur = size_of(b);
         const brs_mf_model& cm = m[b & 1];
-        int rc = brs_mf_fwd_bwd_phases(&cm, loss_kind, users + off, items + off, (const char*)third + off * third_sz, cur,
-                                       reg_weight, stream, 2);
-        if (rc != BRS_OK) return rc;
+        feed.ptrs(b, &u, &i, &t);
+        if ((rc = brs_mf_fwd_bwd_phases(&cm, loss_kind, u, i, t, cur, reg_weight, stream, 2)) != BRS_OK) return rc;
         brs_entity ents[2] = {cm.user, cm.item};
-        const int64_t noff = off + batch;
-        if (noff < n) {
-            const int64_t ncur = (n - noff < batch) ? (n - noff) : batch;
+        if (b + 1 < nb) {
+            if ((rc = feed.before_read(b + 1, st)) != BRS_OK) return rc;
+            const int64_t ncur = size_of(b + 1);
             const brs_mf_model& nm = m[(b + 1) & 1];
+            const int64_t *nu, *ni;
+            const void* nt;
+            feed.ptrs(b + 1, &nu, &ni, &nt);
             const brs_rowset rs[3] = {nm.user.rows, nm.item.rows, nm.item.rows};
-            const long long* idx[3] = {(const long long*)users + noff, (const long long*)items + noff,
-                                       (const long long*)((const char*)third + noff * third_sz)};
+            const long long* idx[3] = {(const long long*)nu, (const long long*)ni, (const long long*)nt};
             const long long nn[3] = {ncur, ncur, ncur};
-            rc = brs_apply_impl_next(ents, 2, &cm.global_bias, 1, 1, opt, cm.ws, 0, out_loss_reg + 4 * b, cur, 3 * cur,
-                                     stream, rs, idx, nn, loss_kind == 0 ? 3 : 2, (int)(b & 1));
+            rc = brs_apply_impl_next(ents, 2, &cm.global_bias, 1, 1, opt, cm.ws, 0, d_out + 4 * b, cur, 3 * cur, stream,
+                                     rs, idx, nn, loss_kind == 0 ? 3 : 2, (int)(b & 1));
         } else {
-            rc = brs_apply_impl_next(ents, 2, &cm.global_bias, 1, 1, opt, cm.ws, 0, out_loss_reg + 4 * b, cur, 3 * cur,
-                                     stream, nullptr, nullptr, nullptr, 0, (int)(b & 1));
+            rc = brs_apply_impl_next(ents, 2, &cm.global_bias, 1, 1, opt, cm.ws, 0, d_out + 4 * b, cur, 3 * cur, stream,
+                                     nullptr, nullptr, nullptr, 0, (int)(b & 1));
         }
         if (rc != BRS_OK) return rc;
+        if ((rc = feed.after_step(b, d_out + 4 * b, st)) != BRS_OK) return rc;
     }
+    return BRS_OK;
+}
+
+// Epoch arrays in HOST memory: batch b+2 is copied to a 4-slot device ring on a private copy stream while
+// batch b computes; each step's record is DMA'd back into pinned memory as soon as it is published.
+struct HostFeed : BatchFeed {
+    static constexpr int R = 4, AHEAD = 2;
+    int device = -1;
+    cudaStream_t copy = nullptr;
+    cudaEvent_t ready[R] = {}, done[R] = {};
+    char* ring = nullptr;       // R slots x 3 arrays x slot_elems x 8 bytes
+    int64_t slot_elems = 0;
+    float* d_out = nullptr;     // device records
+    float* h_rec = nullptr;     // pinned host records
+    int64_t rec_cap = 0;
+    // per call
+    const int64_t *h_users = nullptr, *h_items = nullptr;
+    const char* h_third = nullptr;
+    int64_t n = 0, batch = 0, nb = 0, issued = 0;
+    size_t third_sz = 8;
+
+    int prepare(int64_t batch_, int64_t nb_) {
+        int dev = 0;
+        BRS_CUDA_CHECK(cudaGetDevice(&dev));
+        if (dev != device) {  // first use (or the caller moved to another device): start over
+            device = dev;
+            copy = nullptr;
+            ring = nullptr;
+            d_out = h_rec = nullptr;
+            slot_elems = rec_cap = 0;
+            BRS_CUDA_CHECK(cudaStreamCreateWithFlags(&copy, cudaStreamNonBlocking));
+            for (int k = 0; k < R; ++k) {
+                BRS_CUDA_CHECK(cudaEventCreateWithFlags(&ready[k], cudaEventDisableTiming));
+                BRS_CUDA_CHECK(cudaEventCreateWithFlags(&done[k], cudaEventDisableTiming));
+            }
+        }
+        if (batch_ > slot_elems) {
+            if (ring) BRS_CUDA_CHECK(cudaFree(ring));
+            ring = nullptr;
+            BRS_CUDA_CHECK(cudaMalloc(&ring, (size_t)R * 3 * (size_t)batch_ * 8));
+            slot_elems = batch_;
+        }
+        if (nb_ > rec_cap) {
+            if (d_out) BRS_CUDA_CHECK(cudaFree(d_out));
+            if (h_rec) BRS_CUDA_CHECK(cudaFreeHost(h_rec));
+            d_out = h_rec = nullptr;
+            const int64_t cap = nb_ < 1024 ? 1024 : nb_;
+            BRS_CUDA_CHECK(cudaMalloc(&d_out, (size_t)cap * 16));
+            BRS_CUDA_CHECK(cudaMallocHost(&h_rec, (size_t)cap * 16));
+            rec_cap = cap;
+        }
+        return BRS_OK;
+    }
+    char* slot(int64_t b, int arr) const { return ring + ((size_t)(b % R) * 3 + arr) * (size_t)slot_elems * 8; }
+    int issue(int64_t b) {  // H2D of batch b on the copy stream
+        const int k = (int)(b % R);
+        if (b >= R) BRS_CUDA_CHECK(cudaStreamWaitEvent(copy, done[k], 0));  // batch b-R is done with the slot
+        const int64_t off = b * batch, cur = (b == nb - 1) ? (n - off) : batch;
+        BRS_CUDA_CHECK(cudaMemcpyAsync(slot(b, 0), h_users + off, (size_t)cur * 8, cudaMemcpyHostToDevice, copy));
+        BRS_CUDA_CHECK(cudaMemcpyAsync(slot(b, 1), h_items + off, (size_t)cur * 8, cudaMemcpyHostToDevice, copy));
+        BRS_CUDA_CHECK(cudaMemcpyAsync(slot(b, 2), h_third + (size_t)off * third_sz, (size_t)cur * third_sz,
+                                       cudaMemcpyHostToDevice, copy));
+        BRS_CUDA_CHECK(cudaEventRecord(ready[k], copy));
+        return BRS_OK;
+    }
+    void ptrs(int64_t b, const int64_t** u, const int64_t** i, const void** t) override {
+        *u = (const int64_t*)slot(b, 0);
+        *i = (const int64_t*)slot(b, 1);
+        *t = slot(b, 2);
+    }
+    int before_read(int64_t b, cudaStream_t st) override {
+        while (issued < nb && issued <= b + AHEAD) {
+            int rc = issue(issued);
+            if (rc != BRS_OK) return rc;
+            ++issued;
+        }
+        BRS_CUDA_CHECK(cudaStreamWaitEvent(st, ready[b % R], 0));
+        return BRS_OK;
+    }
+    int after_step(int64_t b, float* d_rec, cudaStream_t st) override {
+        BRS_CUDA_CHECK(cudaEventRecord(done[b % R], st));
+        // the record goes home on the copy stream, so the compute stream never waits for a DMA
+        BRS_CUDA_CHECK(cudaStreamWaitEvent(copy, done[b % R], 0));
+        BRS_CUDA_CHECK(cudaMemcpyAsync(h_rec + 4 * b, d_rec, 16, cudaMemcpyDeviceToHost, copy));
+        return BRS_OK;
+    }
+};
+HostFeed g_host_feed;
+std::mutex g_host_feed_mu;
+}  // namespace
+
+extern "C" int brs_mf_train_batches(const brs_mf_model* model, const brs_opt* opt, int32_t loss_kind,
+                                    const int64_t* users, const int64_t* items, const void* third, int64_t n,
+                                    int64_t batch, float reg_weight, float* out_loss_reg, void* stream) {
+    if (!model || !opt || !users || !items || !third || n < 0 || batch <= 0 || !out_loss_reg) return BRS_ERR_INVALID_ARG;
+    ResidentFeed feed;
+    feed.users = users;
+    feed.items = items;
+    feed.third = (const char*)third;
+    feed.batch = batch;
+    feed.third_sz = loss_kind == 0 ? 8 : 4;
+    return mf_epoch_loop(model, opt, loss_kind, feed, n, batch, reg_weight, out_loss_reg, stream);
+}
+
+extern "C" int brs_mf_train_batches_host(const brs_mf_model* model, const brs_opt* opt, int32_t loss_kind,
+                                         const int64_t* h_users, const int64_t* h_items, const void* h_third,
+                                         int64_t n, int64_t batch, float reg_weight, float* h_out_loss_reg,
+                                         void* stream) {
+    if (!model || !opt || !h_users || !h_items || !h_third || n < 0 || batch <= 0 || !h_out_loss_reg)
+        return BRS_ERR_INVALID_ARG;
+    if (n == 0) return BRS_OK;
+    std::lock_guard<std::mutex> lk(g_host_feed_mu);
+    HostFeed& f = g_host_feed;
+    const int64_t nb = (n + batch - 1) / batch;
+    int rc = f.prepare(batch < n ? batch : n, nb);
+    if (rc != BRS_OK) return rc;
+    f.h_users = h_users;
+    f.h_items = h_items;
+    f.h_third = (const char*)h_third;
+    f.n = n;
+    f.batch = batch;
+    f.nb = nb;
+    f.issued = 0;
+    f.third_sz = loss_kind == 0 ? 8 : 4;
+    rc = mf_epoch_loop(model, opt, loss_kind, f, n, batch, reg_weight, f.d_out, stream);
+    // drain both streams whatever happened: the ring and the pinned records are reused by the next call
+    cudaError_t e1 = cudaStreamSynchronize((cudaStream_t)stream);
+    cudaError_t e2 = cudaStreamSynchronize(f.copy);
+    if (rc != BRS_OK) return rc;
+    BRS_CUDA_CHECK(e1);
+    BRS_CUDA_CHECK(e2);
+    memcpy(h_out_loss_reg, f.h_rec, (size_t)nb * 16);
     return BRS_OK;
 }
 

@@ -158,6 +158,8 @@ class MFEngine(ModelEngine):
         """Inner loop of train_an_epoch over index arrays resident in HBM (one C call,
         2 launches per batch, no host sync until the per-batch results are read)."""
         lib = _lib.load()
+        if all(isinstance(t, torch.Tensor) and not t.is_cuda for t in (users, items, third)):
+            return self._train_batches_host(users, items, third)
         users, items = as_index(users, self.device), as_index(items, self.device)
         third = as_index(third, self.device) if self.loss == "bpr" else as_float(third, self.device)
         n, b = users.numel(), int(self.batch_size)
@@ -170,6 +172,28 @@ class MFEngine(ModelEngine):
                                             _lib.ptr(users), _lib.ptr(items), _lib.ptr(third), n, b, float(self.reg),
                                             _lib.ptr(out), self._stream()), "brs_mf_train_batches")
         res = out.cpu().numpy()
+        self._raise_status(int(res[:, 2].max()))
+        return res
+
+    def _train_batches_host(self, users, items, third):
+        """train_batches for HOST tensors (pin them for full speed): the C loop streams batch b+2 to the
+        device while batch b computes and brings every step's record back; nothing is staged in bulk."""
+        lib = _lib.load()
+        users = users.to(torch.int64).contiguous()
+        items = items.to(torch.int64).contiguous()
+        third = (third.to(torch.int64) if self.loss == "bpr" else third.to(torch.float32)).contiguous()
+        n, b = users.numel(), int(self.batch_size)
+        if items.numel() != n or third.numel() != n:
+            raise ValueError("users / items / third must have the same length")
+        if n == 0:
+            return np.zeros((0, 4), dtype=np.float32)
+        self._ensure_capacity(min(n, b))
+        res = np.zeros(((n + b - 1) // b, 4), dtype=np.float32)
+        with torch.cuda.device(self.device):
+            _lib.check(lib.brs_mf_train_batches_host(self._cmodel, self.optimizer.desc, 0 if self.loss == "bpr" else 1,
+                                                     users.data_ptr(), items.data_ptr(), third.data_ptr(), n, b,
+                                                     float(self.reg), res.ctypes.data, self._stream()),
+                       "brs_mf_train_batches_host")
         self._raise_status(int(res[:, 2].max()))
         return res
 

@@ -193,6 +193,18 @@ int brs_mf_train_batches(const brs_mf_model *model, const brs_opt *opt, int32_t 
                          const int64_t *users, const int64_t *items, const void *third, int64_t n,
                          int64_t batch, float reg_weight, float *out /* brs_step_out[] */, void *stream);
 
+/*
+ * The same loop fed from HOST memory (the loader's side of train_an_epoch, mf.py:132-136, where the
+ * reference moves each batch to the device inside train_single_batch): h_users / h_items / h_third
+ * are host arrays (pinned for full speed; pageable works), h_out is host brs_step_out[n_batches].
+ * Batch b+2 is copied into a device ring on a private copy stream while batch b computes, every step's
+ * record is DMA'd back as soon as it is published.  Returns after the last step completed
+ * (synchronizes `stream`).  One such loop at a time per process.
+ */
+int brs_mf_train_batches_host(const brs_mf_model *model, const brs_opt *opt, int32_t loss_kind,
+                              const int64_t *h_users, const int64_t *h_items, const void *h_third, int64_t n,
+                              int64_t batch, float reg_weight, float *h_out /* brs_step_out[] */, void *stream);
+
 /* MF.predict / MF.forward under no_grad (beta_rec/models/mf.py:57-70): scores[k] = sigmoid(...) */
 int brs_mf_predict(const brs_mf_model *model, const int64_t *users, const int64_t *items, int64_t n,
                    float *scores, void *stream);
