@@ -93,6 +93,14 @@ def lightgcn(nu, ni, n_edges, d, L, b, optimizer, rng_mode):
 
 if __name__ == "__main__":
     B = 65536
+    if len(sys.argv) > 1:  # one short configuration, for an ncu launch list
+        if sys.argv[1] == "neumf":
+            ncf("neumf", 1_000_000, 100_000, 64, 3, B, "sgd", "dense", 1)
+        elif sys.argv[1] == "lightgcn":
+            lightgcn(200_000, 50_000, 4_000_000, 64, 3, B, "adam", "cuda")
+        else:
+            raise SystemExit("usage: bench_models.py [neumf|lightgcn]")
+        sys.exit(0)
     for backend in (1, 0):
         ncf("neumf", 1_000_000, 100_000, 64, 3, B, "sgd", "dense", backend)
     ncf("neumf", 1_000_000, 100_000, 64, 3, B, "adam", "touched", 1)
