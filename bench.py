@@ -188,6 +188,8 @@ def cpu_baseline(a, n_timed=0, budget_s=20.0):
     port.train_single_batch(batches[1])
     if n_timed <= 0:
         n_timed = int(max(3, min(40, budget_s / max(first, 1e-3))))
+    else:  # explicit request (reference arm: --steps): still a bounded sample, a step takes seconds
+        n_timed = int(max(3, min(n_timed, 4.5 * budget_s / max(first, 1e-3))))
     times = []
     for k in range(n_timed):
         t0 = time.time()
