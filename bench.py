@@ -335,9 +335,35 @@ def run_sharded(a, rank, world, local, dev):
         barrier()
         e2e_ms = torch.tensor([s0.elapsed_time(s1)], dtype=torch.float64, device=dev)
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
-        e2e = {"value": n_e2e * a.batch * world / (e2e_ms.item() * 1e-3), "unit": "interactions/s",
-               "h2d_bytes_per_step": 3 * 8 * a.batch, "d2h_bytes_per_step": 16, "steps": n_e2e,
-               "api": "ShardedMFEngine.train_single_batch((users,pos,neg)) with pinned host LongTensors, per rank"}
+        e2e_step = {"value": n_e2e * a.batch * world / (e2e_ms.item() * 1e-3), "unit": "interactions/s",
+                    "h2d_bytes_per_step": 3 * 8 * a.batch, "d2h_bytes_per_step": 16, "steps": n_e2e,
+                    "api": "ShardedMFEngine.train_single_batch((users,pos,neg)) with pinned host LongTensors, per "
+                           "rank: synchronous, one host round trip per step"}
+        e2e = e2e_step
+        if a.route == "none":
+            # epoch-level call: each rank hands its pinned host arrays over whole; the C loop streams batch b+2
+            # in while batch b computes and DMAs every step's record back (same code on every rank, so a
+            # failure is a failure everywhere and all ranks fall back together)
+            try:
+                n_ep = min(nb_host, n_e2e)
+                sl = slice(0, n_ep * a.batch)
+                eng.train_batches(hu[: 4 * a.batch], hp[: 4 * a.batch], hn[: 4 * a.batch])  # warm the ring
+                barrier()
+                s0.record(stream)
+                res = eng.train_batches(hu[sl], hp[sl], hn[sl])
+                s1.record(stream)
+                barrier()
+                assert res.shape[0] == n_ep and not res[:, 2].any()
+                ep_ms = torch.tensor([s0.elapsed_time(s1)], dtype=torch.float64, device=dev)
+                dist.all_reduce(ep_ms, op=dist.ReduceOp.MAX)
+                e2e = {"value": n_ep * a.batch * world / (ep_ms.item() * 1e-3), "unit": "interactions/s",
+                       "h2d_bytes_per_step": 3 * 8 * a.batch, "d2h_bytes_per_step": 16, "steps": n_ep,
+                       "api": "ShardedMFEngine.train_batches(users,pos,neg) on pinned HOST LongTensors per rank "
+                              "(brs_mf_sharded_train_batches_host: per step 3 H2D copies on a copy stream, the "
+                              "sharded step, 16-byte record D2H)",
+                       "per_step_sync_api": e2e_step}
+            except Exception as ex:
+                e2e = dict(e2e_step, epoch_api_error=repr(ex)[:200])
     sampler.stop()
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)

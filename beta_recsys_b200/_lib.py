@@ -158,6 +158,8 @@ _PROTOTYPES = {
                                       C.c_int64, C.c_float, C.c_uint64, _P, _P]),
     "brs_mf_sharded_train_batches": (C.c_int, [C.POINTER(MfSharded), C.POINTER(PeerSync), C.POINTER(Opt), _P, _P, _P,
                                                C.c_int64, C.c_int64, C.c_int64, C.c_float, C.c_uint64, _P, _P]),
+    "brs_mf_sharded_train_batches_host": (C.c_int, [C.POINTER(MfSharded), C.POINTER(PeerSync), C.POINTER(Opt), _P, _P, _P,
+                                               C.c_int64, C.c_int64, C.c_int64, C.c_float, C.c_uint64, _P, _P]),
     "brs_route_triples": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, _P, _P, _P, _P, _P]),
     "brs_gather": (C.c_int, [_P, C.c_int64, C.c_int32, _P, C.c_int64, _P, _P]),
     "brs_scatter_add": (C.c_int, [_P, C.c_int64, C.c_int32, _P, C.c_int64, _P, C.c_float, _P]),

@@ -371,6 +371,51 @@ extern "C" int brs_mf_sharded_train_batches(const brs_mf_sharded* model, const b
     return BRS_OK;
 }
 
+// the sharded epoch loop fed from HOST memory: every rank streams ITS OWN index arrays through the ring
+extern "C" int brs_mf_sharded_train_batches_host(const brs_mf_sharded* model, const brs_peer_sync* sync,
+                                                 const brs_opt* opt, const int64_t* h_users, const int64_t* h_pos_items,
+                                                 const int64_t* h_neg_items, int64_t n, int64_t batch,
+                                                 int64_t global_batch, float reg_weight, uint64_t first_epoch,
+                                                 float* h_out, void* stream) {
+    if (!model || !sync || !opt || !h_users || !h_pos_items || !h_neg_items || !h_out || n < 0 || batch <= 0 ||
+        first_epoch == 0)
+        return BRS_ERR_INVALID_ARG;
+    if (n == 0) return BRS_OK;
+    std::lock_guard<std::mutex> lk(g_host_feed_mu);
+    HostFeed& f = g_host_feed;
+    const int64_t nb = (n + batch - 1) / batch;
+    int rc = f.prepare(batch < n ? batch : n, nb);
+    if (rc != BRS_OK) return rc;
+    f.h_users = h_users;
+    f.h_items = h_pos_items;
+    f.h_third = (const char*)h_neg_items;
+    f.n = n;
+    f.batch = batch;
+    f.nb = nb;
+    f.issued = 0;
+    f.third_sz = 8;
+    cudaStream_t st = (cudaStream_t)stream;
+    uint64_t epoch = first_epoch;
+    for (int64_t b = 0; b < nb && rc == BRS_OK; ++b, epoch += 2) {
+        const int64_t cur = (b == nb - 1) ? (n - b * batch) : batch;
+        const int64_t gb = (cur == batch) ? global_batch : cur * model->world;
+        const int64_t *u, *i;
+        const void* t;
+        if ((rc = f.before_read(b, st)) != BRS_OK) break;
+        f.ptrs(b, &u, &i, &t);
+        rc = brs_mf_sharded_step(model, sync, opt, u, i, (const int64_t*)t, cur, gb, reg_weight, epoch, f.d_out + 4 * b,
+                                 stream);
+        if (rc == BRS_OK) rc = f.after_step(b, f.d_out + 4 * b, st);
+    }
+    cudaError_t e1 = cudaStreamSynchronize(st);
+    cudaError_t e2 = cudaStreamSynchronize(f.copy);
+    if (rc != BRS_OK) return rc;
+    BRS_CUDA_CHECK(e1);
+    BRS_CUDA_CHECK(e2);
+    memcpy(h_out, f.h_rec, (size_t)nb * 16);
+    return BRS_OK;
+}
+
 // ---------------------------------------------------------------------------
 // gather / scatter-add micro-ops (config 5): warp-group per index, 128-bit accesses
 // ---------------------------------------------------------------------------

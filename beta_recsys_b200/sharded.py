@@ -338,13 +338,32 @@ class ShardedMFEngine(object):
         self._epoch += 2
 
     def train_batches(self, users, pos, neg):
-        """Many consecutive steps over this rank's index arrays (route='none'): one C call, five
-        launches per batch, no host involvement until the caller reads the returned records."""
+        """Many consecutive steps over this rank's index arrays (route='none'): one C call, no host
+        involvement until the records are read.  Device tensors: arrays resident in HBM, returns a device
+        tensor [n_batches, 4].  CPU tensors (pin them): the C loop streams batch b+2 through a device ring
+        while batch b computes and DMAs every step's record back; returns a numpy array."""
         if self.route != "none":
             raise _lib.BrsError("train_batches needs route='none' (routing needs a host round trip per batch)")
-        users, pos, neg = (as_index(x, self.device) for x in (users, pos, neg))
+        host = all(isinstance(t, torch.Tensor) and not t.is_cuda for t in (users, pos, neg))
+        if host:
+            users, pos, neg = (t.to(torch.int64).contiguous() for t in (users, pos, neg))
+        else:
+            users, pos, neg = (as_index(x, self.device) for x in (users, pos, neg))
         n, b = users.numel(), self.batch_size
+        if pos.numel() != n or neg.numel() != n:
+            raise ValueError("users / pos / neg must have the same length")
         n_batches = (n + b - 1) // b
+        if host:
+            import numpy as np
+
+            out = np.zeros((n_batches, 4), dtype=np.float32)
+            with torch.cuda.device(self.device):
+                _lib.check(self.lib.brs_mf_sharded_train_batches_host(
+                    C.byref(self._cmodel), C.byref(self._sync), C.byref(self.opt), users.data_ptr(), pos.data_ptr(),
+                    neg.data_ptr(), n, b, b * self.world, float(self.reg), self._epoch + 1, out.ctypes.data,
+                    self._stream()), "brs_mf_sharded_train_batches_host")
+            self._epoch += 2 * n_batches
+            return out
         out = torch.zeros((n_batches, 4), dtype=torch.float32, device=self.device)
         _lib.check(self.lib.brs_mf_sharded_train_batches(
             C.byref(self._cmodel), C.byref(self._sync), C.byref(self.opt), _lib.ptr(users), _lib.ptr(pos), _lib.ptr(neg),

@@ -423,6 +423,14 @@ int brs_mf_sharded_train_batches(const brs_mf_sharded *model, const brs_peer_syn
                                  int64_t batch, int64_t global_batch, float reg_weight, uint64_t first_epoch,
                                  float *out /* brs_step_out[] */, void *stream);
 
+/* the same loop with this rank's index arrays in HOST memory (pinned for full speed) and h_out on the host:
+ * batches are streamed through the device ring of brs_mf_train_batches_host; returns after the last step
+ * completed.  Every rank must call it with the same n / batch / first_epoch. */
+int brs_mf_sharded_train_batches_host(const brs_mf_sharded *model, const brs_peer_sync *sync, const brs_opt *opt,
+                                      const int64_t *h_users, const int64_t *h_pos_items, const int64_t *h_neg_items,
+                                      int64_t n, int64_t batch, int64_t global_batch, float reg_weight,
+                                      uint64_t first_epoch, float *h_out /* brs_step_out[] */, void *stream);
+
 /* stable bucket of (u,i,j) triples by owner(u) = u mod world (the send buffer of the NCCL all-to-all that
  * routes triples to the user-row owner): out_* hold the triples grouped by destination, original order
  * kept inside a group; counts[world] (device int64) receives the group sizes */

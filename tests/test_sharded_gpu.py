@@ -41,7 +41,7 @@ def _zipf(rng, n, size, a=1.05):
     return rng.permutation(n)[rng.choice(n, size=size, p=p)].astype(np.int64)
 
 
-def _worker(rank, world, port, route, optimizer, q, mode=0):
+def _worker(rank, world, port, route, optimizer, q, mode=0, feed="step"):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
@@ -51,7 +51,7 @@ def _worker(rank, world, port, route, optimizer, q, mode=0):
         from beta_recsys_b200.sharded import ShardedMFEngine
 
         _lib.check(_lib.load().brs_debug_set_shard_mode(mode))  # 0: by world size, 1: per-sample peer gathers, 2: pull + staging
-        nu, ni, d, bsz, lr, steps = 5003, 1999, 128, 1024, 0.05, 3
+        nu, ni, d, bsz, lr, steps = 5003, 1999, 128, 1024, 0.05, (6 if feed == "host" else 3)  # 6 > ring depth
         rng = np.random.default_rng(7)  # same on every rank: the global model and all batches
         p = _state(rng, nu, ni, d)
         batches = [[(_zipf(rng, nu, bsz), _zipf(rng, ni, bsz), rng.integers(0, ni, bsz)) for _ in range(world)]
@@ -60,8 +60,16 @@ def _worker(rank, world, port, route, optimizer, q, mode=0):
                              optimizer=optimizer, lr=lr, loss="bpr")}
         eng = ShardedMFEngine(cfg, route=route, state=p)
         st = O.new_opt_state(p, optimizer)
+        if feed == "host":  # the whole epoch from pinned HOST arrays through the streaming C loop
+            mine = [torch.from_numpy(np.concatenate([batches[t][rank][c] for t in range(steps)])).pin_memory()
+                    for c in range(3)]
+            rec = eng.train_batches(*mine)
+            assert rec.shape == (steps, 4) and not rec[:, 2].any()
         for t in range(steps):
-            loss, reg = eng.train_single_batch(tuple(torch.from_numpy(x).cuda() for x in batches[t][rank]))
+            if feed == "host":
+                loss, reg = float(rec[t, 0]), float(rec[t, 1])
+            else:
+                loss, reg = eng.train_single_batch(tuple(torch.from_numpy(x).cuda() for x in batches[t][rank]))
             gu = np.concatenate([b[0] for b in batches[t]])
             gp = np.concatenate([b[1] for b in batches[t]])
             gn = np.concatenate([b[2] for b in batches[t]])
@@ -97,7 +105,7 @@ def _worker(rank, world, port, route, optimizer, q, mode=0):
         dist.destroy_process_group()
 
 
-def _run(world, route, optimizer, mode=0):
+def _run(world, route, optimizer, mode=0, feed="step"):
     if torch.cuda.device_count() < world:
         pytest.skip("needs %d GPUs" % world)
     port = _free_port()
@@ -105,7 +113,7 @@ def _run(world, route, optimizer, mode=0):
     os.environ["PYTHONPATH"] = root + os.pathsep + os.environ.get("PYTHONPATH", "")  # children import tests.*
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, route, optimizer, q, mode)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, route, optimizer, q, mode, feed)) for r in range(world)]
     # children re-import this module by name from the parent's sys.path: keep the repo root first (an
     # earlier test may have put the reference checkout, which has its own `tests` package, in front)
     saved = sys.path[:]
@@ -143,6 +151,13 @@ def test_sharded_world2_adam_first_step():
 def test_sharded_staged_mode_matches_oracle(world, optimizer):
     """mode 2: every unique row pulled once into the staging tables, fused kernel on local memory"""
     _run(world, "none", optimizer, mode=2)
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("world", [1, 2])
+def test_sharded_epoch_from_host_memory(world):
+    """brs_mf_sharded_train_batches_host: per-rank index arrays stay in pinned host memory"""
+    _run(world, "none", "sgd", feed="host")
 
 
 @pytest.mark.timeout(600)
