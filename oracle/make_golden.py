@@ -225,11 +225,26 @@ def gen_lightgcn(name, d, n_layers, optimizer, keep_pro=0.6, n_users=40, n_items
           _opt_state(eng), extra, opt1=opt1)
 
 
+def gen_bench_shapes():
+    """The shapes BASELINE.json's configs 2-4 run at (D = 128 MF, emb 64 / 3-layer NeuMF tower
+    512-256-128-64, D = 128 LightGCN), on small tables.  Prefix cfg_: pinned by the CPU oracle tests."""
+    gen_mf("cfg_mf_bce_d128_adam", 128, "adam", "bce")
+    gen_mf("cfg_mf_bpr_d128_rmsprop", 128, "rmsprop", "bpr", lr=0.01)
+    gen_ncf("cfg_gmf_d128_sgd", "gmf", 128, 3, "sgd", lr=0.01)
+    for opt in ("sgd", "adam"):
+        gen_ncf(f"cfg_neumf_e64_l3_{opt}", "neumf", 64, 3, opt, lr=0.01)
+    gen_ncf("cfg_mlp_e64_l3_sgd", "mlp", 64, 3, "sgd", lr=0.01)
+    gen_lightgcn("cfg_lightgcn_d128_l3_adam", 128, 3, "adam")
+
+
 def main():
     sys.path.insert(0, os.path.dirname(HERE))
     from oracle import ref_shim
 
     ref_shim.install()
+    if "--bench-shapes-only" in sys.argv:  # add the cfg_* files without regenerating the rest
+        return gen_bench_shapes()
+    gen_bench_shapes()
     for d in (64, 128):
         for opt in ("sgd", "adam"):
             gen_mf(f"mf_bpr_d{d}_{opt}", d, opt, "bpr")
