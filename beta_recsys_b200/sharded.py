@@ -2,18 +2,25 @@
 
 New work -- the reference has no distributed path.  Tables are
 row-sharded: ``owner(row) = row mod world``, ``local row = row div world``.  Every rank
-exports its shard (weights, a dense per-shard gradient table, a touched bitmap) through
-CUDA IPC; the kernels address remote memory directly over NVLink.  A step is
+exports its shard (weights; for Adam / RMSprop also a dense per-shard gradient table and a touched
+bitmap) through CUDA IPC; the kernels address remote memory directly over NVLink.  A step
+(``brs_mf_sharded_step``) is
 
     [optional NCCL all-to-all: route triples to the user-row owner]
-    local slot pre-pass + fused fwd/bwd: rows gathered with peer loads, gradients summed in
-                                         a LOCAL compact scratch (no remote atomics per sample)
-    push: one coalesced row per unique touched row -> 128-bit peer REDs into the owner's dense
-          gradient table + red.or of its touched bit
-    flag barrier  (+ exchange of the 3 step sums, added in rank order)
-    optimizer on the rows of the local shard whose bit is set (global_bias is replicated
-          and updated identically on every rank)
-    flag barrier
+    local slot pre-pass: every unique row of the rank's batch gets a compact local slot
+    rows: either gathered per sample with peer loads inside the fused kernel ("direct"), or every
+          UNIQUE row pulled once into local staging tables and the fused kernel run on those
+          ("staged", default from 8 ranks); gradients are summed in a LOCAL compact scratch
+          (no remote atomics per sample)
+    push: one coalesced row of 128-bit peer REDs per unique touched row --
+          SGD: -lr * g straight into the owner's weight rows (flag barrier first: all gathers done);
+          Adam / RMSprop: g into the owner's dense gradient table + red.or of its touched bit,
+          flag barrier, optimizer on the rows of the local shard whose bit is set
+    global_bias is replicated and updated identically on every rank (the first barrier also
+          exchanges the 3 step sums, added in rank order); flag barrier
+
+``train_batches`` runs many steps per C call, from index arrays in HBM or (CPU tensors) streamed
+from pinned host memory through a device ring.
 
 The loss is the mean over the GLOBAL batch (sum of the ranks' batches), exactly what a
 single-GPU run on the concatenated batch computes.
@@ -305,12 +312,6 @@ class ShardedMFEngine(object):
     # -- step ---------------------------------------------------------------- #
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream
-
-    def _barrier(self, with_sums):
-        self._epoch += 1
-        _lib.check(self.lib.brs_peer_barrier(C.byref(self._sync), self._epoch,
-                                             self.arena.ptr("ws") if with_sums else None, self._stream()),
-                   "brs_peer_barrier")
 
     def route_triples(self, users, pos, neg):
         """NCCL all-to-all of triples to the rank owning the user row (north-star routing)."""
