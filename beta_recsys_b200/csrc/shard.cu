@@ -3,7 +3,7 @@
 // New work: the reference has no distributed path.  Tables are
 // row-sharded (owner = row mod world); each rank exports its shard through CUDA IPC and
 // maps its peers', so the hot-path kernels address remote rows directly over NVLink
-// (peer loads / peer REDs / peer atomics) instead of staging them through collectives.
+// (peer loads / peer REDs / red.or on the touched bitmaps) instead of staging them through collectives.
 // This file holds: the exportable allocator + IPC handle helpers, the flag barrier that
 // orders the phases of a step across ranks (and exchanges the step's scalar sums), and the
 // owner bucketing of triples that feeds the (optional)
