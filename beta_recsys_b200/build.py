@@ -44,7 +44,8 @@ def find_nvcc():
 def build(force=False, verbose=False):
     if not force and not _stale():
         return LIB
-    cmd = [find_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB + ".tmp"] + sources()
+    extra = os.environ.get("BRS_NVCC_DEFINES", "").split()  # experiments only, e.g. -DBRS_GS_BLOCK=32
+    cmd = [find_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB + ".tmp"] + sources()
     if verbose:
         print(" ".join(cmd))
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)

@@ -84,17 +84,24 @@ struct brs_l2_policy_cfg {
 };
 const brs_l2_policy_cfg& brs_l2_cfg();
 
-// Gradient-scratch layout.  For dim % 8 == 0 the compact scratch of a table is stored
-// "sector-blocked": [dim/8][capacity][8 floats], i.e. element (slot, col) lives at
-//     ((col >> 3) * capacity + slot) * 8 + (col & 7).
-// The 32-byte sectors of one gradient row are then capacity*32 bytes apart and hash to
-// different L2 slices.  A B200 L2 slice retires ~1 RED sector per clock, and a row-major
-// 512-byte row maps to only TWO slices, so under Zipf indices the hottest row serialised
-// ~36 us of REDs on one slice (round-1 ncu: lts__d_atomic_input_cycles_active max 62%).
-// Other dims keep the row-major [capacity][dim] layout.
+// Gradient-scratch layout.  For dim % BRS_GS_BLOCK == 0 the compact scratch of a table is stored
+// blocked: [dim/BLK][capacity][BLK floats], i.e. element (slot, col) lives at
+//     ((col / BLK) * capacity + slot) * BLK + (col % BLK).
+// Default BLK = 8 ("sector-blocked"): the 32-byte sectors of one gradient row are capacity*32 bytes
+// apart and hash to different L2 slices.  A B200 L2 slice retires ~1 RED sector per clock, and a row-major
+// 512-byte row maps to only TWO slices, so under Zipf indices the hottest row serialised ~36 us of REDs on
+// one slice (round-1 ncu: lts__d_atomic_input_cycles_active max 62%, 31% with BLK = 8).  The price is four
+// times as many L2 requests per warp-level RED (profiles/r01f_fused_kernel_source_stalls.md);
+// -DBRS_GS_BLOCK=32 (one 128-byte line per block, a row over 4 slices) is the round-2 experiment
+// (BRS_NVCC_DEFINES, build.py).  Other dims keep the row-major [capacity][dim] layout.
+#ifndef BRS_GS_BLOCK
+#define BRS_GS_BLOCK 8
+#endif
+static_assert(BRS_GS_BLOCK >= 4 && (BRS_GS_BLOCK & (BRS_GS_BLOCK - 1)) == 0, "block = power of two >= one float4");
 __device__ __forceinline__ size_t gs_off(int dim, int capacity, unsigned slot, int col) {
-    return (dim & 7) ? (size_t)slot * (unsigned)dim + col
-                     : ((size_t)(col >> 3) * (unsigned)capacity + slot) * 8 + (col & 7);
+    return (dim & (BRS_GS_BLOCK - 1))
+               ? (size_t)slot * (unsigned)dim + col
+               : ((size_t)(col / BRS_GS_BLOCK) * (unsigned)capacity + slot) * BRS_GS_BLOCK + (col & (BRS_GS_BLOCK - 1));
 }
 
 // 128-bit fire-and-forget scatter-add (sm_90+): one L2 reduction per 16 bytes.
