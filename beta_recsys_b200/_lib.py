@@ -46,9 +46,14 @@ class DenseParam(C.Structure):
                 ("numel", C.c_int64)]
 
 
+class MfPlan(C.Structure):
+    _fields_ = [("buf", C.c_void_p), ("bytes", C.c_int64), ("batch_capacity", C.c_int64),
+                ("user_capacity", C.c_int32), ("item_capacity", C.c_int32)]
+
+
 class MfModel(C.Structure):
     _fields_ = [("user", Entity), ("item", Entity), ("global_bias", DenseParam), ("ws", C.c_void_p),
-                ("user_rows_alt", Rowset), ("item_rows_alt", Rowset)]
+                ("user_rows_alt", Rowset), ("item_rows_alt", Rowset), ("plan", MfPlan * 2), ("user_stage", C.c_void_p)]
 
 
 NCF_GMF, NCF_MLP, NCF_NEUMF = 0, 1, 2
@@ -101,7 +106,7 @@ class MfSharded(C.Structure):
                 ("pull_user_bias", C.c_void_p), ("pull_item_bias", C.c_void_p)]
 
 
-EXTRA_STRUCTS = {"brs_csr": Csr, "brs_lightgcn_model": LightGCNModel, "brs_ncf_model": NcfModel, "brs_mf_peer_tables": MfPeerTables, "brs_peer_sync": PeerSync,
+EXTRA_STRUCTS = {"brs_mf_plan": MfPlan, "brs_csr": Csr, "brs_lightgcn_model": LightGCNModel, "brs_ncf_model": NcfModel, "brs_mf_peer_tables": MfPeerTables, "brs_peer_sync": PeerSync,
                  "brs_mf_sharded": MfSharded}
 
 _P = C.c_void_p
@@ -115,7 +120,6 @@ _PROTOTYPES = {
     "brs_mf_bpr_fwd_bwd": (C.c_int, [C.POINTER(MfModel), _P, _P, _P, C.c_int64, C.c_float, _P]),
     "brs_mf_bpr_prepare": (C.c_int, [C.POINTER(MfModel), _P, _P, _P, C.c_int64, _P]),
     "brs_mf_bpr_fwd_bwd_prepared": (C.c_int, [C.POINTER(MfModel), _P, _P, _P, C.c_int64, C.c_float, _P]),
-    "brs_debug_set_mf_variant": (C.c_int, [C.c_int]),
     "brs_debug_set_l2_policy": (C.c_int, [C.c_int, C.c_int, C.c_int]),
     "brs_mf_bce_fwd_bwd": (C.c_int, [C.POINTER(MfModel), _P, _P, _P, C.c_int64, C.c_float, _P]),
     "brs_mf_apply": (C.c_int, [C.POINTER(MfModel), C.POINTER(Opt), C.c_int64, _P, _P]),
@@ -124,6 +128,15 @@ _PROTOTYPES = {
     "brs_mf_train_batches_host": (C.c_int, [C.POINTER(MfModel), C.POINTER(Opt), C.c_int32, _P, _P, _P, C.c_int64,
                                        C.c_int64, C.c_float, _P, _P]),
     "brs_mf_predict": (C.c_int, [C.POINTER(MfModel), _P, _P, C.c_int64, _P, _P]),
+    "brs_mf_plan_bytes": (C.c_int64, [C.c_int64, C.c_int32, C.c_int32]),
+    "brs_mf_plan_build": (C.c_int, [C.POINTER(MfModel), C.c_int32, C.c_int32, _P, _P, _P, C.c_int64, _P]),
+    "brs_mf_step_planned": (C.c_int, [C.POINTER(MfModel), C.c_int32, C.POINTER(Opt), C.c_int32, C.c_int64, C.c_float,
+                                      _P, _P]),
+    "brs_debug_set_mf_rows_only": (C.c_int, [C.c_int]),
+    "brs_debug_mf_rows_profile": (C.c_int, [_P, C.c_int]),
+    "brs_debug_set_mf_rows_shape": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "brs_mf_step": (C.c_int, [C.POINTER(MfModel), C.POINTER(Opt), C.c_int32, _P, _P, _P, C.c_int64, C.c_float, _P,
+                              _P]),
     "brs_ncf_fwd_bwd": (C.c_int, [C.POINTER(NcfModel), _P, _P, _P, C.c_int64, _P]),
     "brs_ncf_apply": (C.c_int, [C.POINTER(NcfModel), C.POINTER(Opt), C.c_int64, _P, _P]),
     "brs_ncf_predict": (C.c_int, [C.POINTER(NcfModel), _P, _P, C.c_int64, _P, _P]),
@@ -184,7 +197,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the ABI lost a symbol
         fn.restype = res
         fn.argtypes = args
-    if lib.brs_abi_version() != 1:
+    if lib.brs_abi_version() != 2:
         raise BrsError("libbrs_b200.so ABI version mismatch")
     _lib = lib
     return lib
@@ -197,6 +210,22 @@ def check(status, what=""):
         if status == -3:
             msg += ": " + lib.brs_last_cuda_error().decode()
         raise BrsError("%s failed: %s" % (what or "libbrs_b200 call", msg))
+
+
+def step_record(out):
+    """brs_step_out -> (loss, regularizer, status) from a float32[4] device tensor (one D2H copy, the
+    reference's two .item() syncs) -- status is an int32 bit mask stored in the third word."""
+    rec = out.detach().cpu().numpy()
+    return float(rec[0]), float(rec[1]), int(rec.view("int32")[2])
+
+
+def step_records_status(res):
+    """OR of the status words of a float32 [n, 4] numpy array of brs_step_out records."""
+    import numpy as np
+
+    if res.shape[0] == 0:
+        return 0
+    return int(np.bitwise_or.reduce(np.ascontiguousarray(res).view(np.int32)[:, 2]))
 
 
 def ptr(t):

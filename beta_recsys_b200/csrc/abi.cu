@@ -22,7 +22,8 @@ int brs_mf_fwd_bwd_phases(const brs_mf_model* model, int loss_kind, const int64_
 namespace {
 char g_cuda_err[512] = "";
 std::mutex g_err_mu;
-int g_sm_count = 0;
+constexpr int kMaxDevices = 64;
+int g_sm_count[kMaxDevices] = {};
 }  // namespace
 
 void brs_set_cuda_error(cudaError_t e, const char* what, int line) {
@@ -31,16 +32,20 @@ void brs_set_cuda_error(cudaError_t e, const char* what, int line) {
     (void)cudaGetLastError();
 }
 
-int brs_sm_count() {
-    if (g_sm_count == 0) {
-        int dev = 0, n = 0;
-        if (cudaGetDevice(&dev) == cudaSuccess &&
-            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
-            g_sm_count = n;
-        else
-            g_sm_count = 148;  // B200
+int brs_sm_count() {  // of the CURRENT device (cached per device)
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) {
+        (void)cudaGetLastError();
+        return 148;  // B200
     }
-    return g_sm_count;
+    if (g_sm_count[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+            g_sm_count[dev] = n;
+        else
+            g_sm_count[dev] = 148;
+    }
+    return g_sm_count[dev];
 }
 
 namespace {
@@ -136,8 +141,84 @@ struct ResidentFeed : BatchFeed {  // the whole epoch's arrays already live in H
 
 // Per batch: fused fwd/bwd + apply, 2 launches when the slot pre-pass of batch b+1 can ride in the apply
 // launch of batch b (alternate rowsets + touched-rows optimizer), else the plain 3-launch sequence.
+// side stream + events of the row-owner epoch loop, one set per device
+struct PlanPipe {
+    cudaStream_t side = nullptr;
+    cudaEvent_t planned[2] = {}, freed[2] = {};
+    int init() {
+        if (side) return BRS_OK;
+        BRS_CUDA_CHECK(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+        for (int k = 0; k < 2; ++k) {
+            BRS_CUDA_CHECK(cudaEventCreateWithFlags(&planned[k], cudaEventDisableTiming));
+            BRS_CUDA_CHECK(cudaEventCreateWithFlags(&freed[k], cudaEventDisableTiming));
+        }
+        return BRS_OK;
+    }
+};
+PlanPipe g_plan_pipe[kMaxDevices];
+std::mutex g_plan_pipe_mu;
+
+// Row-owner loop (mf_rowwise.cu): the index plan of batch b+1 (claim / scan / fill: reads only the index
+// arrays) is built on a side stream while batch b's two row kernels run on `stream`; plans and rowsets
+// alternate, events order the two streams.  With a single plan everything is issued on `stream`.
+int mf_epoch_loop_rowwise(const brs_mf_model* model, const brs_opt* opt, int loss_kind, BatchFeed& feed, int64_t n,
+                          int64_t batch, float reg_weight, float* d_out, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t nb = (n + batch - 1) / batch;
+    auto size_of = [&](int64_t b) { return (b == nb - 1) ? (n - b * batch) : batch; };
+    const int64_t *u, *i;
+    const void* t;
+    int rc;
+    const bool two = model->plan[1].buf && model->user_rows_alt.slot_map && model->item_rows_alt.slot_map;
+    if (!two) {
+        for (int64_t b = 0; b < nb; ++b) {
+            if ((rc = feed.before_read(b, st)) != BRS_OK) return rc;
+            feed.ptrs(b, &u, &i, &t);
+            if ((rc = brs_mf_step(model, opt, loss_kind, u, i, t, size_of(b), reg_weight, d_out + 4 * b, stream)) != BRS_OK)
+                return rc;
+            if ((rc = feed.after_step(b, d_out + 4 * b, st)) != BRS_OK) return rc;
+        }
+        return BRS_OK;
+    }
+    int dev = 0;
+    BRS_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= kMaxDevices) return BRS_ERR_UNSUPPORTED;
+    std::lock_guard<std::mutex> lk(g_plan_pipe_mu);
+    PlanPipe& pp = g_plan_pipe[dev];
+    if ((rc = pp.init()) != BRS_OK) return rc;
+    // whatever `stream` did before (previous steps released the rowsets) precedes the first plan
+    BRS_CUDA_CHECK(cudaEventRecord(pp.freed[0], st));
+    BRS_CUDA_CHECK(cudaEventRecord(pp.freed[1], st));
+    auto plan = [&](int64_t b) -> int {
+        const int k = (int)(b & 1);
+        BRS_CUDA_CHECK(cudaStreamWaitEvent(pp.side, pp.freed[k], 0));
+        int r = feed.before_read(b, pp.side);
+        if (r != BRS_OK) return r;
+        feed.ptrs(b, &u, &i, &t);
+        r = brs_mf_plan_build(model, k, loss_kind, u, i, t, size_of(b), pp.side);
+        if (r != BRS_OK) return r;
+        BRS_CUDA_CHECK(cudaEventRecord(pp.planned[k], pp.side));
+        return BRS_OK;
+    };
+    if (nb > 0 && (rc = plan(0)) != BRS_OK) return rc;
+    for (int64_t b = 0; b < nb; ++b) {
+        const int k = (int)(b & 1);
+        if (b + 1 < nb && (rc = plan(b + 1)) != BRS_OK) break;
+        BRS_CUDA_CHECK(cudaStreamWaitEvent(st, pp.planned[k], 0));
+        if ((rc = brs_mf_step_planned(model, k, opt, loss_kind, size_of(b), reg_weight, d_out + 4 * b, stream)) != BRS_OK) break;
+        BRS_CUDA_CHECK(cudaEventRecord(pp.freed[k], st));
+        if ((rc = feed.after_step(b, d_out + 4 * b, st)) != BRS_OK) break;
+    }
+    // the side stream's work is ordered before anything issued on `stream` afterwards
+    cudaEvent_t& last = pp.planned[0];
+    if (cudaEventRecord(last, pp.side) == cudaSuccess) (void)cudaStreamWaitEvent(st, last, 0);
+    return rc;
+}
+
 int mf_epoch_loop(const brs_mf_model* model, const brs_opt* opt, int loss_kind, BatchFeed& feed, int64_t n, int64_t batch,
                   float reg_weight, float* d_out, void* stream) {
+    if (model->plan[0].buf && model->user_stage)
+        return mf_epoch_loop_rowwise(model, opt, loss_kind, feed, n, batch, reg_weight, d_out, stream);
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t nb = (n + batch - 1) / batch;
     auto size_of = [&](int64_t b) { return (b == nb - 1) ? (n - b * batch) : batch; };
@@ -215,12 +296,8 @@ struct HostFeed : BatchFeed {
     int prepare(int64_t batch_, int64_t nb_) {
         int dev = 0;
         BRS_CUDA_CHECK(cudaGetDevice(&dev));
-        if (dev != device) {  // first use (or the caller moved to another device): start over
+        if (dev != device) {  // first use on this device (the feed object itself is per device)
             device = dev;
-            copy = nullptr;
-            ring = nullptr;
-            d_out = h_rec = nullptr;
-            slot_elems = rec_cap = 0;
             BRS_CUDA_CHECK(cudaStreamCreateWithFlags(&copy, cudaStreamNonBlocking));
             for (int k = 0; k < R; ++k) {
                 BRS_CUDA_CHECK(cudaEventCreateWithFlags(&ready[k], cudaEventDisableTiming));
@@ -278,8 +355,16 @@ struct HostFeed : BatchFeed {
         return BRS_OK;
     }
 };
-HostFeed g_host_feed;
+HostFeed g_host_feed[kMaxDevices];  // one ring / copy stream / record buffer per device
 std::mutex g_host_feed_mu;
+HostFeed* host_feed_for_current_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) {
+        (void)cudaGetLastError();
+        return nullptr;
+    }
+    return &g_host_feed[dev];
+}
 }  // namespace
 
 extern "C" int brs_mf_train_batches(const brs_mf_model* model, const brs_opt* opt, int32_t loss_kind,
@@ -303,7 +388,9 @@ extern "C" int brs_mf_train_batches_host(const brs_mf_model* model, const brs_op
         return BRS_ERR_INVALID_ARG;
     if (n == 0) return BRS_OK;
     std::lock_guard<std::mutex> lk(g_host_feed_mu);
-    HostFeed& f = g_host_feed;
+    HostFeed* fp = host_feed_for_current_device();
+    if (!fp) return BRS_ERR_NO_DEVICE;
+    HostFeed& f = *fp;
     const int64_t nb = (n + batch - 1) / batch;
     int rc = f.prepare(batch < n ? batch : n, nb);
     if (rc != BRS_OK) return rc;
@@ -382,7 +469,9 @@ extern "C" int brs_mf_sharded_train_batches_host(const brs_mf_sharded* model, co
         return BRS_ERR_INVALID_ARG;
     if (n == 0) return BRS_OK;
     std::lock_guard<std::mutex> lk(g_host_feed_mu);
-    HostFeed& f = g_host_feed;
+    HostFeed* fp = host_feed_for_current_device();
+    if (!fp) return BRS_ERR_NO_DEVICE;
+    HostFeed& f = *fp;
     const int64_t nb = (n + batch - 1) / batch;
     int rc = f.prepare(batch < n ? batch : n, nb);
     if (rc != BRS_OK) return rc;

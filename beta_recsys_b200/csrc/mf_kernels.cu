@@ -25,6 +25,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "mf_math.cuh"
 
 int brs_assign_slots(const brs_rowset* rs, const long long* const* idx, const long long* n, int n_arrays,
                      brs_step_ws* ws, cudaStream_t st);
@@ -35,7 +36,6 @@ constexpr int kThreads = 128;
 constexpr int kWarps = kThreads / 32;
 constexpr int kTile = 32;  // samples per staged index tile (double-buffered)
 
-enum { LOSS_BPR = 0, LOSS_BCE = 1 };
 enum { SHARD_NONE = 0, SHARD_DIRECT = 1, SHARD_STAGED = 2 };
 
 struct MfPeerTables {  // one rank's shard, as seen from this process (device-resident array of these)
@@ -92,13 +92,6 @@ struct __align__(16) IdxTile {
     long long b[kTile];
     long long c[kTile];  // neg ids, or ratings in the first kTile*4 bytes
 };
-
-__device__ __forceinline__ float4 f4_zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
-__device__ __forceinline__ float4 f4_scale(float s, float4 a) { return make_float4(s * a.x, s * a.y, s * a.z, s * a.w); }
-__device__ __forceinline__ float4 f4_fma(float s, float4 a, float4 b) {
-    return make_float4(fmaf(s, a.x, b.x), fmaf(s, a.y, b.y), fmaf(s, a.z, b.z), fmaf(s, a.w, b.w));
-}
-__device__ __forceinline__ float f4_dot(float4 a, float4 b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
 
 // everything one lane holds for one in-flight sample
 template <int VPL, int LOSS>
@@ -187,14 +180,7 @@ __device__ __forceinline__ void sample_load(const MfArgs& a, const IdxTile& T, i
     }
 }
 
-// FAST = true evaluates the sigmoid / log chain with the MUFU approximations (__expf, __logf,
-// __fdividef): ~1e-6 relative on the scores, used only by experimental variants
-template <bool FAST>
-__device__ __forceinline__ float sig_(float x) {
-    return FAST ? __fdividef(1.0f, 1.0f + __expf(-x)) : sigmoidf_(x);
-}
-
-template <int LPR, int VPL, bool FULL, int LOSS, int SHARD, bool FAST>
+template <int LPR, int VPL, bool FULL, int LOSS, int SHARD>
 __device__ __forceinline__ void sample_finish(const MfArgs& a, const Sample<VPL, LOSS>& x, int gl, int D, float bg,
                                               unsigned long long pol_s, float& loss_acc, float& reg_acc,
                                               float& gb_acc) {
@@ -212,31 +198,8 @@ __device__ __forceinline__ void sample_finish(const MfArgs& a, const Sample<VPL,
     dp = group_sum<LPR>(dp);
     if (LOSS == LOSS_BPR) dn = group_sum<LPR>(dn);
 
-    float cu_i, cu_j = 0.f;  // d loss / d z for the (u,i) and (u,j) scores
-    float loss_k;
-    if (LOSS == LOSS_BPR) {
-        // mf.py:43-48 then torch_engine.py:104-105
-        const float sp = sig_<FAST>(dp + x.bu + x.bi + bg);
-        const float sn = sig_<FAST>(dn + x.bu + x.bj + bg);
-        const float d = sp - sn;
-        float dx;
-        if (FAST) {
-            const float e = __expf(-fabsf(d));  // one exp serves both logsigmoid(d) and sigmoid(-d)
-            loss_k = -(fminf(d, 0.0f) - __logf(1.0f + e));
-            dx = -a.inv_b * (d >= 0.f ? __fdividef(e, 1.0f + e) : __fdividef(1.0f, 1.0f + e));
-        } else {
-            loss_k = -logsigmoidf_(d);
-            dx = -a.inv_b / (1.0f + expf(d));  // d/dx of -mean(logsigmoid(x))
-        }
-        cu_i = dx * sp * (1.0f - sp);
-        cu_j = -dx * sn * (1.0f - sn);
-    } else {
-        // nn.BCELoss: logs clamped at -100; backward (s-r)/max((1-s)s, 1e-12)/B
-        const float sc_ = sigmoidf_(dp + x.bu + x.bi + bg);
-        loss_k = -(x.rating * fmaxf(logf(sc_), -100.f) + (1.0f - x.rating) * fmaxf(log1pf(-sc_), -100.f));
-        const float ds = (sc_ - x.rating) / fmaxf((1.0f - sc_) * sc_, 1e-12f) * a.inv_b;
-        cu_i = ds * sc_ * (1.0f - sc_);
-    }
+    float cu_i, cu_j, loss_k;  // d loss / d z for the (u,i) and (u,j) scores
+    mf_sample_coef<LOSS>(dp + x.bu + x.bi + bg, dn + x.bu + x.bj + bg, x.rating, a.inv_b, cu_i, cu_j, loss_k);
     if (!x.valid) return;
 
     // regularizer numerator (mf.py:49-54), one forward call per score
@@ -311,7 +274,7 @@ __device__ __forceinline__ bool stage_tile(const MfArgs& a, long long t, IdxTile
     return used_tma;
 }
 
-template <int LPR, int VPL, bool FULL, int LOSS, int SHARD, int UNROLL, int MINB, bool FAST>
+template <int LPR, int VPL, bool FULL, int LOSS, int SHARD, int UNROLL, int MINB>
 __global__ void __launch_bounds__(kThreads, MINB) mf_fwd_bwd_kernel(const MfArgs a) {
     constexpr int SPW = 32 / LPR;
     __shared__ IdxTile s_tile[2];
@@ -370,7 +333,7 @@ __global__ void __launch_bounds__(kThreads, MINB) mf_fwd_bwd_kernel(const MfArgs
                 sample_load<LPR, VPL, FULL, LOSS, SHARD>(a, T, b0 + q * kWarps * SPW + grp, tile_n, gl, D, pol_g, x[q]);
 #pragma unroll
             for (int q = 0; q < UNROLL; ++q)
-                sample_finish<LPR, VPL, FULL, LOSS, SHARD, FAST>(a, x[q], gl, D, bg, pol_s, loss_acc, reg_acc, gb_acc);
+                sample_finish<LPR, VPL, FULL, LOSS, SHARD>(a, x[q], gl, D, bg, pol_s, loss_acc, reg_acc, gb_acc);
         }
         __syncthreads();  // everyone is done with s_tile[buf] before it is refilled
     }
@@ -445,16 +408,6 @@ int grid_for(const void* kernel, long long work_blocks) {
     return (int)(g < 1 ? 1 : g);
 }
 
-// experimental lane mappings for D = 128, picked at run time with BRS_MF_VARIANT (tools/sweep_mf.py)
-int g_mf_variant = -1;
-int mf_variant() {
-    if (g_mf_variant < 0) {
-        const char* e = getenv("BRS_MF_VARIANT");
-        g_mf_variant = e ? atoi(e) : 0;
-    }
-    return g_mf_variant;
-}
-
 // how the row-sharded step reads remote rows: SHARD_DIRECT gathers them per sample with peer loads inside
 // the fused kernel; SHARD_STAGED pulls each unique row once into local staging tables first.
 // BRS_SHARD_MODE=1|2 or brs_debug_set_shard_mode
@@ -475,30 +428,13 @@ template <int LOSS, int SHARD = SHARD_NONE>
 int launch_fwd_bwd(const MfArgs& a, cudaStream_t st) {
     const int D = a.dim;
     const long long n_tiles = (a.batch + kTile - 1) / kTile;
-#define BRS_LAUNCHX(LPR, VPL, FULL, UNROLL, MINB, FAST)                                 \
+#define BRS_LAUNCHX(LPR, VPL, FULL, UNROLL, MINB)                                       \
     do {                                                                                \
-        auto k = mf_fwd_bwd_kernel<LPR, VPL, FULL, LOSS, SHARD, UNROLL, MINB, FAST>;    \
+        auto k = mf_fwd_bwd_kernel<LPR, VPL, FULL, LOSS, SHARD, UNROLL, MINB>;          \
         k<<<grid_for((const void*)k, n_tiles), kThreads, 0, st>>>(a);                   \
     } while (0)
-#define BRS_LAUNCH(LPR, VPL, FULL) BRS_LAUNCHX(LPR, VPL, FULL, 1, ((VPL) <= 2 ? 8 : (SHARD ? 4 : 5)), false)
+#define BRS_LAUNCH(LPR, VPL, FULL) BRS_LAUNCHX(LPR, VPL, FULL, 1, ((VPL) <= 2 ? 8 : (SHARD ? 4 : 5)))
     if (D % 4 != 0 || D <= 0 || D > 512) return BRS_ERR_UNSUPPORTED;
-    if (D == 128 && LOSS == LOSS_BPR && mf_variant() != 0) {
-        switch (mf_variant()) {
-            case 1: BRS_LAUNCHX(8, 4, true, 1, 6, false); break;
-            case 2: BRS_LAUNCHX(16, 2, true, 2, 5, false); break;
-            case 3: BRS_LAUNCHX(16, 2, true, 2, 6, false); break;
-            case 4: BRS_LAUNCHX(32, 1, true, 4, 5, false); break;
-            case 5: BRS_LAUNCHX(8, 4, true, 1, 4, false); break;
-            case 6: BRS_LAUNCHX(8, 4, true, 1, 5, true); break;
-            case 7: BRS_LAUNCHX(8, 4, true, 1, 6, true); break;
-            case 8: BRS_LAUNCHX(16, 2, true, 2, 6, true); break;
-            case 9: BRS_LAUNCHX(4, 8, true, 1, 3, false); break;
-            case 10: BRS_LAUNCHX(8, 4, true, 2, 3, false); break;
-            default: return BRS_ERR_INVALID_ARG;
-        }
-        BRS_CUDA_CHECK(cudaGetLastError());
-        return BRS_OK;
-    }
     switch (D) {  // VPL = 4 float4 per lane wherever D allows: a warp instruction serves 32/LPR samples
         case 4: BRS_LAUNCH(1, 1, true); break;
         case 8: BRS_LAUNCH(1, 2, true); break;
@@ -607,11 +543,6 @@ int brs_mf_fwd_bwd_phases(const brs_mf_model* model, int loss_kind, const int64_
     if (loss_kind == LOSS_BPR) return launch_fwd_bwd<LOSS_BPR>(a, st);
     if (loss_kind == LOSS_BCE) return launch_fwd_bwd<LOSS_BCE>(a, st);
     return BRS_ERR_INVALID_ARG;
-}
-
-extern "C" int brs_debug_set_mf_variant(int variant) {
-    g_mf_variant = variant < 0 ? 0 : variant;
-    return BRS_OK;
 }
 
 extern "C" int brs_mf_bpr_fwd_bwd(const brs_mf_model* model, const int64_t* users, const int64_t* pos_items,

@@ -13,6 +13,7 @@
 // The last block to finish also applies the ws-sourced scalar (MF global bias),
 // publishes {loss, regularizer, status} and resets the step scratch.
 #include "common.cuh"
+#include "opt_math.cuh"
 
 int brs_assign_slots(const brs_rowset* rs, const long long* const* idx, const long long* n, int n_arrays,
                      brs_step_ws* ws, cudaStream_t st);
@@ -98,63 +99,6 @@ __global__ void __launch_bounds__(kThreads) assign_slots_kernel(const AssignArgs
     assign_slots_block(a, blockIdx.y, blockIdx.x, gridDim.x);
 }
 
-// ---------------------------------------------------------------------------
-// optimizer math
-// ---------------------------------------------------------------------------
-struct OptScalars {  // per-step scalars, computed in double like torch does on the host
-    float lr;
-    float one_minus_b1, b2, one_minus_b2;
-    float step_size;  // lr / (1 - b1^t)
-    float bc2_sqrt;   // sqrt(1 - b2^t)
-    float eps;
-    float alpha, one_minus_alpha;
-};
-
-struct OptParams {
-    int kind;
-    double lr, beta1, beta2, eps, alpha;
-};
-
-__device__ __forceinline__ OptScalars make_scalars(const OptParams& o, long long t) {
-    OptScalars s;
-    s.lr = (float)o.lr;
-    s.one_minus_b1 = (float)(1.0 - o.beta1);
-    s.b2 = (float)o.beta2;
-    s.one_minus_b2 = (float)(1.0 - o.beta2);
-    const double bc1 = 1.0 - pow(o.beta1, (double)t);
-    const double bc2 = 1.0 - pow(o.beta2, (double)t);
-    s.step_size = (float)(o.lr / bc1);
-    s.bc2_sqrt = (float)sqrt(bc2);
-    s.eps = (float)o.eps;
-    s.alpha = (float)o.alpha;
-    s.one_minus_alpha = (float)(1.0 - o.alpha);
-    return s;
-}
-
-// one element of torch.optim's single-tensor update
-template <int KIND>
-__device__ __forceinline__ void opt_elem(float& p, float g, float& m, float& v, const OptScalars& s) {
-    if (KIND == BRS_SGD) {
-        p -= s.lr * g;  // sgd.py: param.add_(grad, alpha=-lr)
-    } else if (KIND == BRS_ADAM) {
-        m = m + (g - m) * s.one_minus_b1;                // exp_avg.lerp_(grad, 1-beta1)
-        v = v * s.b2 + s.one_minus_b2 * g * g;           // mul_(beta2).addcmul_(grad, grad, 1-beta2)
-        const float denom = sqrtf(v) / s.bc2_sqrt + s.eps;
-        p -= s.step_size * (m / denom);                  // addcdiv_(exp_avg, denom, -step_size)
-    } else {
-        v = v * s.alpha + s.one_minus_alpha * g * g;     // rmsprop.py, momentum 0, not centered
-        p -= s.lr * (g / (sqrtf(v) + s.eps));
-    }
-}
-
-template <int KIND>
-__device__ __forceinline__ void opt_elem4(float4& p, const float4& g, float4& m, float4& v, const OptScalars& s) {
-    opt_elem<KIND>(p.x, g.x, m.x, v.x, s);
-    opt_elem<KIND>(p.y, g.y, m.y, v.y, s);
-    opt_elem<KIND>(p.z, g.z, m.z, v.z, s);
-    opt_elem<KIND>(p.w, g.w, m.w, v.w, s);
-}
-
 struct ApplyArgs {
     brs_entity ent[kMaxEntities];
     int n_ent;
@@ -173,6 +117,9 @@ struct ApplyArgs {
     int n_apply_blocks;   // 0: every block applies
     int parity;           // which ws->err_pending slot belongs to the batch being applied
     AssignArgs next;
+    // row-owner MF step (mf_rowwise.cu): the touched rows (slot >= 0) were already updated by their owners,
+    // the sweep only moves the others (g = 0); an index error voids the whole step
+    int skip_touched;
 };
 
 // one touched row of one table: scratch row `slot` -> weight row `row`
@@ -276,7 +223,9 @@ __device__ __forceinline__ void dense_params_update(const ApplyArgs& a, const Op
 // run by the LAST block only (every other block has finished reading ws by then)
 template <int KIND>
 __device__ void finalize(const ApplyArgs& a, const OptScalars& s) {
-    if (a.dense_grad_from_ws && a.n_dense > 0 && threadIdx.x == 0) {
+    const unsigned int status = a.ws ? (a.ws->err_flag | a.ws->err_pending[a.parity & 1]) : 0u;
+    const bool void_step = a.skip_touched && status != 0u;  // row-owner step: nothing was updated
+    if (a.dense_grad_from_ws && a.n_dense > 0 && threadIdx.x == 0 && !void_step) {
         const brs_dense_param& dp = a.dense[0];
         const float g = a.ws->g_global_bias;
         float w = dp.weight[0];
@@ -293,7 +242,7 @@ __device__ void finalize(const ApplyArgs& a, const OptScalars& s) {
             a.out[0] = (float)(a.ws->loss_sum * a.inv_batch);
             a.out[1] = (float)(a.ws->reg_sum * a.inv_batch);
             // 0 ok | 1 index out of range | 2 touched-row capacity overflow
-            a.out[2] = (float)(a.ws->err_flag | a.ws->err_pending[a.parity & 1]);
+            ((int*)a.out)[2] = (int)status;
             a.out[3] = 0.f;
         }
         if (a.advance_step) {
@@ -302,7 +251,7 @@ __device__ void finalize(const ApplyArgs& a, const OptScalars& s) {
             a.ws->loss_sum = 0.0;
             a.ws->reg_sum = 0.0;
             a.ws->g_global_bias = 0.f;
-            a.ws->step += 1;
+            if (!void_step) a.ws->step += 1;
         }
         a.ws->ticket = 0u;
     }
@@ -397,7 +346,7 @@ __global__ void __launch_bounds__(kThreads) rows_apply_kernel(const ApplyArgs a)
 // grid-stride over float4 vectors (or scalars when dim % 4 != 0) of one table
 template <int KIND>
 __device__ __forceinline__ void sweep_table(const brs_table& tb, const int* __restrict__ slot_map, int cap,
-                                            const OptScalars& s, long long tid, long long nthreads) {
+                                            const OptScalars& s, long long tid, long long nthreads, bool skip_touched) {
     const int d = tb.dim;
     if ((d & 3) == 0) {
         const int vpr = d >> 2;
@@ -407,7 +356,9 @@ __device__ __forceinline__ void sweep_table(const brs_table& tb, const int* __re
             const long long row = shift >= 0 ? (i >> shift) : (nvec < (1ll << 31) ? (long long)((unsigned)i / (unsigned)vpr) : i / vpr);
             const int slot = slot_map[row];
             float4 gv = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (slot >= 0) {
+            if (skip_touched) {
+                if (slot >= 0) continue;
+            } else if (slot >= 0) {
                 float4* gp = (float4*)(tb.grad + gs_off(d, cap, (unsigned)slot, (int)(i - row * vpr) * 4));
                 gv = *gp;
                 *gp = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -427,7 +378,9 @@ __device__ __forceinline__ void sweep_table(const brs_table& tb, const int* __re
             const long long row = i / d;
             const int slot = slot_map[row];
             float g = 0.f;
-            if (slot >= 0) {
+            if (skip_touched) {
+                if (slot >= 0) continue;
+            } else if (slot >= 0) {
                 float* gp = tb.grad + (long long)slot * d + (i - row * d);
                 g = *gp;
                 *gp = 0.f;
@@ -451,10 +404,14 @@ __global__ void __launch_bounds__(kThreads) dense_sweep_kernel(const ApplyArgs a
     const OptScalars s = s_opt;
     const long long tid = (long long)blockIdx.x * kThreads + threadIdx.x;
     const long long nthreads = (long long)gridDim.x * kThreads;
-    for (int e = 0; e < a.n_ent; ++e)
-        for (int k = 0; k < a.ent[e].n_tables; ++k)
-            sweep_table<KIND>(a.ent[e].table[k], a.ent[e].rows.slot_map, a.ent[e].rows.capacity, s, tid, nthreads);
-    dense_params_update<KIND>(a, s);
+    const bool void_step = a.skip_touched && a.ws && a.ws->err_pending[a.parity & 1] != 0u;
+    if (!void_step) {
+        for (int e = 0; e < a.n_ent; ++e)
+            for (int k = 0; k < a.ent[e].n_tables; ++k)
+                sweep_table<KIND>(a.ent[e].table[k], a.ent[e].rows.slot_map, a.ent[e].rows.capacity, s, tid, nthreads,
+                                  a.skip_touched != 0);
+        dense_params_update<KIND>(a, s);
+    }
     if (a.ws) {
         if (last_block(a)) finalize<KIND>(a, s);
     }
@@ -786,6 +743,35 @@ int brs_apply_impl_next(const brs_entity* ents, int n_ent, const brs_dense_param
         case BRS_RMSPROP: return launch_apply<BRS_RMSPROP>(a, opt->mode, max_rows_hint, st);
         default: return BRS_ERR_UNSUPPORTED;
     }
+}
+
+// row-owner MF step, BRS_DENSE Adam / RMSprop: move every row that is NOT in the batch with g = 0 (the
+// reference's dense optimizers do), finalise the step through ws, then release the rowsets
+int brs_dense_sweep_untouched(const brs_entity* ents, int n_ent, const brs_dense_param* dense, int n_dense,
+                              int dense_grad_from_ws, const brs_opt* opt, void* ws, float* out, long long batch,
+                              int parity, void* stream) {
+    if (!opt || !ws || opt->kind == BRS_SGD) return BRS_ERR_INVALID_ARG;
+    int rc = validate_entities(ents, n_ent, opt->kind);
+    if (rc != BRS_OK) return rc;
+    rc = validate_dense(dense, n_dense, opt->kind, dense_grad_from_ws != 0);
+    if (rc != BRS_OK) return rc;
+    ApplyArgs a;
+    memset(&a, 0, sizeof(a));
+    for (int e = 0; e < n_ent; ++e) a.ent[e] = ents[e];
+    a.n_ent = n_ent;
+    for (int k = 0; k < n_dense; ++k) a.dense[k] = dense[k];
+    a.n_dense = n_dense;
+    a.dense_grad_from_ws = dense_grad_from_ws;
+    fill_opt(a, opt);
+    a.ws = (brs_step_ws*)ws;
+    a.out = out;
+    a.inv_batch = batch > 0 ? 1.0 / (double)batch : 0.0;
+    a.advance_step = 1;
+    a.parity = parity & 1;
+    a.skip_touched = 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (opt->kind == BRS_ADAM) return launch_apply<BRS_ADAM>(a, BRS_DENSE, 0, st);
+    return launch_apply<BRS_RMSPROP>(a, BRS_DENSE, 0, st);
 }
 
 extern "C" int brs_rows_sgd(const brs_entity* entities, int32_t n_entities, double lr, void* stream) {

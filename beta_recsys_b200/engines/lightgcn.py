@@ -177,7 +177,7 @@ class LightGCNEngine(ModelEngine):
                                             _lib.ptr(pos), _lib.ptr(neg), b, self._stream()), "brs_lightgcn_fwd_bwd")
         _lib.check(lib.brs_lightgcn_apply(self._cmodel, self.optimizer.desc, b, _lib.ptr(self._out), self._stream()),
                    "brs_lightgcn_apply")
-        loss, _, status, _ = self._out.tolist()
+        loss, _, status = _lib.step_record(self._out)
         if int(status) & 1:
             raise IndexError("index out of range in self")
         return loss

@@ -87,19 +87,37 @@ class MFEngine(ModelEngine):
         self._gb_state = opt.add_param("global_bias", m.global_bias.data)
         self._ws = torch.zeros(_lib.STEP_WS_BYTES, dtype=torch.uint8, device=dev)
         self._out = torch.zeros(4, dtype=torch.float32, device=dev)
-        self._refresh_struct()
+        # "rows" (default): the row-owner step of csrc/mf_rowwise.cu; "scratch": round 1's fused kernel +
+        # gradient-scratch apply (csrc/mf_kernels.cu, rows_apply.cu), kept as a second implementation
+        mc = self.config["model"]
+        self._step_impl = mc["step_impl"] if "step_impl" in mc else "rows"
+        if self._step_impl not in ("rows", "scratch"):
+            raise ValueError("step_impl must be 'rows' or 'scratch'")
+        self._plan_batch = 0
+        self._refresh_struct(b)
         m._engine = self
 
-    def _refresh_struct(self):
+    def _refresh_struct(self, b=None):
         self._cmodel = _lib.MfModel(self._user.struct, self._item.struct,
                                     dense_param(self.model.global_bias.data, None, self._gb_state),
                                     _lib.ptr(self._ws), self._user.alt_rowset(), self._item.alt_rowset())
+        if self._step_impl != "rows":
+            return
+        lib, dev = _lib.load(), self.device
+        self._plan_batch = max(int(b or 0), self._plan_batch, 1)
+        nbytes = lib.brs_mf_plan_bytes(self._plan_batch, self._user.capacity, self._item.capacity)
+        self._plans = [torch.zeros(nbytes, dtype=torch.uint8, device=dev) for _ in range(2)]
+        self._user_stage = torch.empty((self._user.capacity, self.model.emb_dim), dtype=torch.float32, device=dev)
+        for k in range(2):
+            self._cmodel.plan[k] = _lib.MfPlan(_lib.ptr(self._plans[k]), nbytes, self._plan_batch, self._user.capacity,
+                                               self._item.capacity)
+        self._cmodel.user_stage = _lib.ptr(self._user_stage)
 
     def _ensure_capacity(self, b):
         grew = self._user.ensure_capacity(b)
         grew = self._item.ensure_capacity(2 * b) or grew
-        if grew:
-            self._refresh_struct()
+        if grew or (self._step_impl == "rows" and b > self._plan_batch):
+            self._refresh_struct(b)
 
     @staticmethod
     def _raise_status(status):
@@ -122,6 +140,20 @@ class MFEngine(ModelEngine):
 
     def _launch_step(self, batch_data, out):
         lib = _lib.load()
+        if self.loss not in ("bpr", "bce"):
+            raise RuntimeError(f"Unsupported loss type {self.loss}, try other options: 'bpr' or 'bce'")
+        if self._step_impl == "rows":
+            users, items, third = batch_data
+            users, items = as_index(users, self.device), as_index(items, self.device)
+            third = as_index(third, self.device) if self.loss == "bpr" else as_float(third, self.device)
+            b = users.numel()
+            if items.numel() != b or third.numel() != b:
+                raise ValueError("users / items / third must have the same length")
+            self._ensure_capacity(b)
+            _lib.check(lib.brs_mf_step(self._cmodel, self.optimizer.desc, 0 if self.loss == "bpr" else 1,
+                                       _lib.ptr(users), _lib.ptr(items), _lib.ptr(third), b, float(self.reg),
+                                       _lib.ptr(out), self._stream()), "brs_mf_step")
+            return
         if self.loss == "bpr":
             users, pos, neg = batch_data
             users, pos, neg = (as_index(t, self.device) for t in (users, pos, neg))
@@ -147,10 +179,10 @@ class MFEngine(ModelEngine):
                    "brs_mf_apply")
 
     def train_single_batch(self, batch_data):
-        """mf.py:92-119: one batch -> (loss: float, regularizer: float); two kernels + one 16-byte D2H."""
+        """mf.py:92-119: one batch -> (loss: float, regularizer: float); one C call + one 16-byte D2H."""
         assert hasattr(self, "model"), "Please specify the exact model !"
         self._launch_step(batch_data, self._out)
-        loss, reg, status, _ = self._out.tolist()  # the reference's two .item() syncs, in one copy
+        loss, reg, status = _lib.step_record(self._out)  # the reference's two .item() syncs, in one copy
         self._raise_status(status)
         return loss, reg
 
@@ -172,7 +204,7 @@ class MFEngine(ModelEngine):
                                             _lib.ptr(users), _lib.ptr(items), _lib.ptr(third), n, b, float(self.reg),
                                             _lib.ptr(out), self._stream()), "brs_mf_train_batches")
         res = out.cpu().numpy()
-        self._raise_status(int(res[:, 2].max()))
+        self._raise_status(_lib.step_records_status(res))
         return res
 
     def _train_batches_host(self, users, items, third):
@@ -194,7 +226,7 @@ class MFEngine(ModelEngine):
                                                      users.data_ptr(), items.data_ptr(), third.data_ptr(), n, b,
                                                      float(self.reg), res.ctypes.data, self._stream()),
                        "brs_mf_train_batches_host")
-        self._raise_status(int(res[:, 2].max()))
+        self._raise_status(_lib.step_records_status(res))
         return res
 
     def train_an_epoch(self, train_loader, epoch_id):

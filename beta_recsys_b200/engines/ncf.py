@@ -233,7 +233,7 @@ class _NcfEngine(ModelEngine):
                                        self._stream()), "brs_ncf_fwd_bwd")
         _lib.check(lib.brs_ncf_apply(self._cmodel, self.optimizer.desc, b, _lib.ptr(self._out), self._stream()),
                    "brs_ncf_apply")
-        loss, _, status, _ = self._out.tolist()
+        loss, _, status = _lib.step_record(self._out)
         self._raise_status(status)
         return loss
 
@@ -251,7 +251,7 @@ class _NcfEngine(ModelEngine):
                                              _lib.ptr(ratings), n, b, _lib.ptr(out), self._stream()),
                    "brs_ncf_train_batches")
         res = out.cpu().numpy()
-        self._raise_status(int(res[:, 2].max()))
+        self._raise_status(_lib.step_records_status(res))
         return res
 
     def train_an_epoch(self, train_loader, epoch_id):

@@ -375,7 +375,7 @@ class ShardedMFEngine(object):
 
     def train_single_batch(self, batch, global_batch=None):
         self.launch_step(batch, global_batch)
-        loss, reg, status, _ = self._out.tolist()
+        loss, reg, status = _lib.step_record(self._out)
         if int(status) & 1:
             raise IndexError("index out of range in self")
         if status:

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define BRS_ABI_VERSION 1
+#define BRS_ABI_VERSION 2
 
 typedef enum brs_status {
     BRS_OK = 0,
@@ -113,12 +113,24 @@ typedef struct brs_dense_param {
 typedef struct brs_step_out {
     float loss;         /* batch loss (mean over the batch) */
     float regularizer;  /* MF regularizer (mf.py:49-54); 0 for other models */
-    float status;       /* 0 ok | 1 an index was outside its table (the reference raises IndexError)
+    int32_t status;     /* bit mask: 0 ok | 1 an index was outside its table (the reference raises IndexError)
                            | 2 touched-row list capacity exceeded */
     float reserved;
 } brs_step_out;
 
 /* ---- MF: beta_rec/models/mf.py (MF module + MFEngine) ---- */
+/* Device scratch for the index plan of ONE batch (row-owner step): the batch's samples grouped by user
+ * row (the user stream) and its (sample, item) entries grouped by item row (the item stream), one
+ * contiguous segment per unique row.  Built by brs_mf_plan_build from the index arrays alone (no table
+ * access), consumed by brs_mf_step_planned.  buf: brs_mf_plan_bytes(...) bytes, zero-filled once by the
+ * caller. */
+typedef struct brs_mf_plan {
+    void *buf;
+    int64_t bytes;
+    int64_t batch_capacity;               /* samples per batch the plan can hold */
+    int32_t user_capacity, item_capacity; /* = the rowset capacities it was sized for */
+} brs_mf_plan;
+
 typedef struct brs_mf_model {
     brs_entity user;              /* table[0] = user_emb [U,D], table[1] = user_bias [U,1] */
     brs_entity item;              /* table[0] = item_emb [I,D], table[1] = item_bias [I,1] */
@@ -127,6 +139,12 @@ typedef struct brs_mf_model {
     /* optional second set of slot maps / lists / counters (same capacities; slot_map NULL = absent).  With
      * them brs_mf_train_batches runs the slot pre-pass of batch b+1 inside the apply launch of batch b. */
     brs_rowset user_rows_alt, item_rows_alt;
+    /* row-owner step (brs_mf_step / brs_mf_train_batches): per-batch index plans (one per
+     * rowset parity; plan[1] may be absent) and the staging copy of the batch's pre-step user rows
+     * ([user rowset capacity, dim] fp32).  plan[0].buf == NULL or user_stage == NULL selects the
+     * gradient-scratch path (brs_mf_*_fwd_bwd + brs_mf_apply) everywhere. */
+    brs_mf_plan plan[2];
+    float *user_stage;
 } brs_mf_model;
 
 /* one rank's MF shard as seen from the calling process (pointers mapped through CUDA IPC / NVLink peer
@@ -163,9 +181,6 @@ int brs_mf_bpr_prepare(const brs_mf_model *model, const int64_t *users, const in
 int brs_mf_bpr_fwd_bwd_prepared(const brs_mf_model *model, const int64_t *users, const int64_t *pos_items,
                                 const int64_t *neg_items, int64_t batch, float reg_weight, void *stream);
 
-/* diagnostics: select an experimental lane mapping of the fused MF kernel (0 = production default;
- * also settable with the BRS_MF_VARIANT environment variable); see tools/sweep_mf.py */
-int brs_debug_set_mf_variant(int variant);
 /* diagnostics: L2 eviction priority (0 normal, 1 evict_first, 2 evict_last) used for the embedding-row
  * gathers, the compact gradient scratch, and the weight-row updates of the apply kernels */
 int brs_debug_set_l2_policy(int gather, int scratch, int weight);
@@ -204,6 +219,48 @@ int brs_mf_train_batches(const brs_mf_model *model, const brs_opt *opt, int32_t 
 int brs_mf_train_batches_host(const brs_mf_model *model, const brs_opt *opt, int32_t loss_kind,
                               const int64_t *h_users, const int64_t *h_items, const void *h_third, int64_t n,
                               int64_t batch, float reg_weight, float *h_out /* brs_step_out[] */, void *stream);
+
+/*
+ * Row-owner MF step (round 2; replaces the fwd_bwd + apply pair on the training path).  The same maths and
+ * the same batch-synchronous semantics as brs_mf_*_fwd_bwd + brs_mf_apply (beta_rec/models/mf.py:92-119),
+ * organised so that every touched table row is read from HBM once and written once, with no gradient
+ * scratch and no atomics on the common path:
+ *   plan   (index-only, brs_mf_plan_build): slot per unique row, samples grouped by user row and
+ *          (sample, item) entries grouped by item row, one contiguous segment per row;
+ *   users  (equal ranges of the user stream per lane group): gathers the three rows of each sample,
+ *          evaluates score / loss / d loss once per block of 4 samples, keeps the user-row gradient in
+ *          registers while the user stays the same, hands (coefficient, user slot) to the item stream,
+ *          stages the PRE-step user row and writes the updated row in place;
+ *   items  (equal ranges of the item stream): sums coefficient * staged user row in registers and writes
+ *          the updated item row in place; the last block applies the global bias step and publishes
+ *          brs_step_out.
+ * Rows whose segment crosses a range boundary (Zipf head) combine their partial sums through table.grad
+ * (row-major [capacity][dim] here) and the last part to arrive applies the update.
+ * Adam / RMSprop in BRS_DENSE mode additionally sweep the untouched rows with g = 0 (reference-exact).
+ * On an out-of-range index the step publishes status 1 and leaves every parameter untouched.
+ */
+int64_t brs_mf_plan_bytes(int64_t batch_capacity, int32_t user_capacity, int32_t item_capacity);
+/* which = 0/1 selects {user.rows,item.rows,plan[0]} or {user_rows_alt,item_rows_alt,plan[1]};
+ * loss_kind 0 = bpr (third = neg item ids, int64), 1 = bce (third = ratings, float) */
+int brs_mf_plan_build(const brs_mf_model *model, int32_t which, int32_t loss_kind, const int64_t *users,
+                      const int64_t *items, const void *third, int64_t batch, void *stream);
+int brs_mf_step_planned(const brs_mf_model *model, int32_t which, const brs_opt *opt, int32_t loss_kind,
+                        int64_t batch, float reg_weight, float *out /* brs_step_out */, void *stream);
+/* plan_build(which = 0) + step_planned on one stream: MFEngine.train_single_batch */
+int brs_mf_step(const brs_mf_model *model, const brs_opt *opt, int32_t loss_kind, const int64_t *users,
+                const int64_t *items, const void *third, int64_t batch, float reg_weight,
+                float *out /* brs_step_out */, void *stream);
+
+/* diagnostics: ring stages (2..4) and warps per block (2 | 4) of the two row kernels (dim 128 only), the
+ * cap on resident blocks per SM (0 = default: rings take about half of the L1 / shared-memory array), and
+ * log2 of the nominal work-unit length (0..3; plans built afterwards use it) */
+int brs_debug_set_mf_rows_shape(int stages, int warps_per_block, int blocks_per_sm, int unit_shift);
+/* diagnostics (per-kernel timing on a FIXED plan; leaves the step incomplete): 0 = both row kernels,
+ * 1 = users kernel only, 2 = items kernel only */
+int brs_debug_set_mf_rows_only(int which);
+/* diagnostics, only in builds with -DBRS_ROWS_PROFILE (else BRS_ERR_UNSUPPORTED): per-warp clock64 phase
+ * counters of the users kernel, 8 int64 per warp; the first call (host_out NULL) allocates the buffer */
+int brs_debug_mf_rows_profile(long long *host_out, int n_warps);
 
 /* MF.predict / MF.forward under no_grad (beta_rec/models/mf.py:57-70): scores[k] = sigmoid(...) */
 int brs_mf_predict(const brs_mf_model *model, const int64_t *users, const int64_t *items, int64_t n,

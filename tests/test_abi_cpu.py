@@ -36,7 +36,7 @@ def test_library_exports_every_declared_symbol(lib_path):
     lib = ctypes.CDLL(lib_path)
     for name in declared_functions():
         assert hasattr(lib, name), "missing export: " + name
-    assert lib.brs_abi_version() == 1
+    assert lib.brs_abi_version() == 2
     lib.brs_strerror.restype = ctypes.c_char_p
     assert lib.brs_strerror(0) == b"ok"
     assert b"unsupported" in lib.brs_strerror(-2)
