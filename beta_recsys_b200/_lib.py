@@ -133,7 +133,6 @@ _PROTOTYPES = {
     "brs_mf_step_planned": (C.c_int, [C.POINTER(MfModel), C.c_int32, C.POINTER(Opt), C.c_int32, C.c_int64, C.c_float,
                                       _P, _P]),
     "brs_debug_set_mf_rows_only": (C.c_int, [C.c_int]),
-    "brs_debug_mf_rows_profile": (C.c_int, [_P, C.c_int]),
     "brs_debug_set_mf_rows_shape": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "brs_mf_step": (C.c_int, [C.POINTER(MfModel), C.POINTER(Opt), C.c_int32, _P, _P, _P, C.c_int64, C.c_float, _P,
                               _P]),

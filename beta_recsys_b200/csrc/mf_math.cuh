@@ -36,3 +36,26 @@ __device__ __forceinline__ void mf_sample_coef(float zp, float zn, float rating,
         cu_j = 0.f;
     }
 }
+
+// Same quantities with the SFU intrinsics (ex2 / lg2 / rcp approximations, relative error ~1e-6) for the BPR
+// chain of the row-owner kernels, where the chain's ~120 instructions per block were a visible share of the
+// issue slots.  Every argument stays in a benign range (|d| < 1, 1 + e in (1, 2]), so the results differ from
+// the ATen-style evaluation above by ~1e-7 absolute -- two orders below the 1e-5 parity budget.  BCE keeps the
+// precise path: its log(1 - s) is ill-conditioned for saturated scores.
+template <int LOSS>
+__device__ __forceinline__ void mf_sample_coef_fast(float zp, float zn, float rating, float inv_b, float& cu_i,
+                                                    float& cu_j, float& loss_k) {
+    if (LOSS == LOSS_BPR) {
+        const float sp = __fdividef(1.0f, 1.0f + __expf(-zp));
+        const float sn = __fdividef(1.0f, 1.0f + __expf(-zn));
+        const float d = sp - sn;
+        const float e = __expf(-fabsf(d));
+        const float t = __fdividef(1.0f, 1.0f + e);  // sigmoid(|d|)
+        loss_k = __logf(1.0f + e) - fminf(d, 0.0f);  // -logsigmoid(d)
+        const float dx = -inv_b * (d < 0.f ? t : e * t);  // -sigmoid(-d) / B
+        cu_i = dx * sp * (1.0f - sp);
+        cu_j = -dx * sn * (1.0f - sn);
+    } else {
+        mf_sample_coef<LOSS>(zp, zn, rating, inv_b, cu_i, cu_j, loss_k);
+    }
+}

@@ -11,22 +11,23 @@
 //                     (block sum + one atomicAdd on the stream cursor; the order of segments is free)
 //            fill     one thread per sample: its record in the USER stream (samples grouped by user row)
 //                     and its one or two entries in the ITEM stream (entries grouped by item row)
-//   users  the user stream is cut into equal ranges, one per lane group (a whole warp at dim 128): per
-//          block of 4 samples the three rows are gathered with 128-bit loads (next block prefetched in
-//          registers), the dots are reduced by a halving butterfly so that the sigmoid / loss chain runs
-//          once per block, the user-row gradient is accumulated in registers while the user stays the
-//          same; at the end of a row: PRE-step row -> staging table, updated row -> table, in place;
-//          per sample (coefficient, user slot) -> the item stream
+//   users  one warp per work unit of the user stream (about 16 samples; a unit never cuts a short row):
+//          per block of 4 samples the rows are gathered by cp.async (one warp instruction per 512-byte
+//          row at dim 128; the next block is in flight while this one is processed), the block's 8 dots
+//          are reduced by ONE transposing butterfly so that the sigmoid / loss chain runs once per block,
+//          the user-row gradient is accumulated in registers while the user stays the same; at the end
+//          of a row: PRE-step row -> staging table, updated row -> table, in place; per sample
+//          (coefficient, user slot) -> the item stream
 //   items  same walk over the item stream: sum of coefficient * staged user row in registers, updated
 //          item row in place; last block: global-bias step + brs_step_out
 //
 // Batch-synchronous semantics hold because item rows are only written by `items` (after every gather
 // of `users` has completed: kernel boundary), `items` reads user rows only from the staging copy, and a
-// user row is written only after all of its samples were read.  Rows whose segment crosses a range
-// boundary (always the Zipf head) add their partial sums into the row-major gradient scratch with 128-bit
-// REDs; the last part to arrive (ticket) applies the update.  Round 1 did one 512-byte RED per sample-row
-// (196 608 per batch at config 2; RED issue rate was the limiter) plus a second pass over the touched
-// rows and 2.9x the compulsory DRAM traffic; here at most two rows per lane group RED.
+// user row is written only after all of its samples were read.  Rows longer than a unit (the Zipf head)
+// are cut at unit boundaries: the parts add their partial sums into the row-major gradient scratch with
+// 128-bit REDs and the last part to arrive (ticket) applies the update.  Round 1 did one 512-byte RED per
+// sample-row (196 608 per batch at config 2; RED issue rate was the limiter) plus a second pass over the
+// touched rows and 2.9x the compulsory DRAM traffic.
 #include <string.h>
 
 #include "common.cuh"
@@ -39,18 +40,27 @@ int brs_dense_sweep_untouched(const brs_entity* ents, int n_ent, const brs_dense
 
 namespace {
 
-constexpr int kThreads = 128;
-constexpr int kWarps = kThreads / 32;
 constexpr int kPlanThreads = 256;
 constexpr int kPlanWarps = kPlanThreads / 32;
 #define BRS_SLOT_OVERFLOW (-3)
+
+// Hot rows.  A 512-byte row lives in two L2 slices and a slice serves about one 32-byte sector per clock, so
+// a row that is gathered thousands of times in one step (Zipf head: the hottest item is ~10% of a batch, the
+// hottest user likewise) serialises the whole kernel on those two slices (round-2 profile: both row kernels
+// sat at ~35 us with every pipe idle, whatever their instruction count or occupancy).  The plan therefore
+// lists the rows gathered at least kHotReads times and every CTA of the row kernels keeps them in shared
+// memory; records carry (hot index + 1) in spare high bits, 0 = gather from global memory as usual.
+constexpr int kHotRows = 32;
+constexpr int kHotReads = 384;
+constexpr int kSlotBits = 20;  // s_a.y / ipair.y = user slot | (hot + 1) << kSlotBits
+constexpr int kPosBits = 24;   // s_b.x / s_b.y   = item-stream position | (hot + 1) << kPosBits
 
 // ---------------------------------------------------------------------------
 // plan buffer carve-up (host and device agree through this one function)
 // ---------------------------------------------------------------------------
 struct PlanView {
     int* hdr;        // [64]: 0 = samples in the user stream, 1 = entries in the item stream (segment cursors),
-                     //       2 / 3 = work-unit counters of the users / items kernels
+                     //       4 / 5 = hot user / item rows found by this plan (may exceed kHotRows: clamp)
     int* u_slot;     // [B]   user slot of sample s (-1: sample dropped)
     int* u_rank;     // [B]   rank of s inside its user segment
     int* i_slot;     // [2B]  c*B + s
@@ -59,14 +69,16 @@ struct PlanView {
     int* i_cnt;      // [Ci]
     int2* u_seg;     // [Cu]  {begin, end} of the slot's segment in the user stream
     int2* i_seg;     // [Ci]
+    int* u_hot;      // [Cu]  index of the slot's row in the hot list, -1 = not hot
+    int* i_hot;      // [Ci]
+    int* u_hotlist;  // [kHotRows] user SLOTS whose staged row the items kernel keeps in shared memory
+    int* i_hotlist;  // [kHotRows] item ROW IDS whose row the users kernel keeps in shared memory
     int* u_ticket;   // [Cu]  parts of a multi-part row that have finished (zero between steps)
     int* i_ticket;   // [Ci]
     int4* s_a;       // [B]   user stream position p -> {user row, user slot, pos item, neg item | rating bits}
     int4* s_b;       // [B]   p -> {item-stream position of the pos entry, of the neg entry, segment begin, end}
     int4* i_a;       // [2B]  item stream position q -> {item row, item slot, segment begin, end}
     float2* ipair;   // [2B]  q -> {coefficient, user slot bits}   (written by the users kernel)
-    int* u_cuts;     // [B+2]  work-unit boundaries of the user stream (see mf_plan_cuts_kernel)
-    int* i_cuts;     // [2B+2] ... of the item stream
     size_t bytes;
 };
 
@@ -88,14 +100,16 @@ __host__ __device__ inline PlanView plan_view(void* buf, long long B, int Cu, in
     BRS_CARVE(i_cnt, int, Ci)
     BRS_CARVE(u_seg, int2, Cu)
     BRS_CARVE(i_seg, int2, Ci)
+    BRS_CARVE(u_hot, int, Cu)
+    BRS_CARVE(i_hot, int, Ci)
+    BRS_CARVE(u_hotlist, int, kHotRows)
+    BRS_CARVE(i_hotlist, int, kHotRows)
     BRS_CARVE(u_ticket, int, Cu)
     BRS_CARVE(i_ticket, int, Ci)
     BRS_CARVE(s_a, int4, B)
     BRS_CARVE(s_b, int4, B)
     BRS_CARVE(i_a, int4, 2 * B)
     BRS_CARVE(ipair, float2, 2 * B)
-    BRS_CARVE(u_cuts, int, B + 2)
-    BRS_CARVE(i_cuts, int, 2 * B + 2)
 #undef BRS_CARVE
     v.bytes = o;
     return v;
@@ -112,7 +126,7 @@ struct PlanArgs {
     const void* third;  // neg ids (int64) or ratings (float)
     long long batch;
     int n_cols;         // 2 = bpr (pos, neg), 1 = bce
-    int unit_shift;     // nominal work-unit length = 1 << unit_shift stream positions
+    int hot_reads;      // a row gathered at least this often per step is hot (INT_MAX: packing impossible, none)
     unsigned int* err;  // ws->err_pending[which]
 };
 
@@ -146,8 +160,8 @@ __global__ void __launch_bounds__(kPlanThreads) mf_plan_claim_kernel(const PlanA
     if (blockIdx.x == 0 && threadIdx.x == 0) {  // segment cursors of this plan (consumed by the next kernel)
         a.pv.hdr[0] = 0;
         a.pv.hdr[1] = 0;
-        a.pv.hdr[2] = 0;
-        a.pv.hdr[3] = 0;
+        a.pv.hdr[4] = 0;
+        a.pv.hdr[5] = 0;
     }
     for (long long it = 0; it < n_iter; ++it) {
         const long long s = it * stride + (long long)blockIdx.x * kPlanThreads + threadIdx.x;
@@ -242,6 +256,11 @@ __global__ void __launch_bounds__(kPlanThreads) mf_plan_segment_kernel(const Pla
     const brs_rowset& rs = ent == 0 ? a.urs : a.irs;
     int* cnt = ent == 0 ? a.pv.u_cnt : a.pv.i_cnt;
     int2* seg = ent == 0 ? a.pv.u_seg : a.pv.i_seg;
+    int* hot = ent == 0 ? a.pv.u_hot : a.pv.i_hot;
+    int* hotlist = ent == 0 ? a.pv.u_hotlist : a.pv.i_hotlist;
+    // a user row is gathered once per (sample, item) entry by the items kernel, an item row once per entry
+    // by the users kernel
+    const int reads_per = ent == 0 ? a.n_cols : 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int n = *rs.count;
     if (n > rs.capacity) n = rs.capacity;
@@ -271,6 +290,13 @@ __global__ void __launch_bounds__(kPlanThreads) mf_plan_segment_kernel(const Pla
             const int begin = s_base + s_w[warp] + incl - c;
             seg[k] = make_int2(begin, begin + c);
             cnt[k] = 0;
+            int h = -1;
+            if (c >= (a.hot_reads + reads_per - 1) / reads_per) {
+                h = atomicAdd(a.pv.hdr + 4 + ent, 1);
+                if (h < kHotRows) hotlist[h] = ent == 0 ? k : rs.list[k];
+                else h = -1;
+            }
+            hot[k] = h;
         }
         __syncthreads();
     }
@@ -296,52 +322,42 @@ __global__ void __launch_bounds__(kPlanThreads) mf_plan_fill_kernel(const PlanAr
         const int2 is = a.pv.i_seg[si];
         const int qi = is.x + a.pv.i_rank[s];
         a.pv.i_a[qi] = make_int4(i, si, is.x, is.y);
-        int qj = -1;
+        int qj = -1, pj = -1;
         if (two) {
             const int sj = a.pv.i_slot[B + s];
             const int2 js = a.pv.i_seg[sj];
             qj = js.x + a.pv.i_rank[B + s];
             a.pv.i_a[qj] = make_int4(second, sj, js.x, js.y);
+            pj = qj | ((a.pv.i_hot[sj] + 1) << kPosBits);
         }
-        a.pv.s_a[p] = make_int4(u, su, i, second);
-        a.pv.s_b[p] = make_int4(qi, qj, us.x, us.y);
+        a.pv.s_a[p] = make_int4(u, su | ((a.pv.u_hot[su] + 1) << kSlotBits), i, second);
+        a.pv.s_b[p] = make_int4(qi | ((a.pv.i_hot[si] + 1) << kPosBits), pj, us.x, us.y);
     }
 }
 
-// Work units.  A stream [0, n) is nominally cut every L = 2^unit_shift positions; unit k of a stream is
-// [cut[k], cut[k+1]).  A nominal boundary that falls inside a SHORT segment (<= kSnap positions: almost every
-// row) moves to that segment's end, so the row is owned by exactly one unit and never takes the RED + ticket
-// path; inside a LONG segment (the Zipf head) it moves up to the next multiple of kSnap, so a long row is
-// cut every kSnap positions whatever L is.  A unit is therefore at most L + kSnap - 1 positions long.
-constexpr int kSnap = 8;
-constexpr int kSnapShift = 3;
-__global__ void __launch_bounds__(kPlanThreads) mf_plan_cuts_kernel(const PlanArgs a) {
-    const int ent = blockIdx.y;
-    const int n = a.pv.hdr[ent];
-    const int4* rec = ent == 0 ? a.pv.s_b : a.pv.i_a;  // .z / .w = segment begin / end in both streams
-    int* cuts = ent == 0 ? a.pv.u_cuts : a.pv.i_cuts;
-    const int L = 1 << a.unit_shift;
-    const int units = (n + L - 1) >> a.unit_shift;
-    for (int k = blockIdx.x * kPlanThreads + threadIdx.x; k <= units; k += gridDim.x * kPlanThreads) {
-        const long long pos = (long long)k << a.unit_shift;
-        int c;
-        if (pos >= n) {
-            c = n;
-        } else {
-            const int4 r = rec[pos];
-            const int sb = r.z, se = r.w;
-            if ((int)pos <= sb) c = (int)pos;                 // already on a row boundary
-            else if (se - sb <= kSnap) c = se;                // short row: whole row goes to the earlier unit
-            else c = min(se, ((int)pos + kSnap - 1) & ~(kSnap - 1));
-        }
-        cuts[k] = c;
-    }
+// Work units.  A stream [0, n) is nominally cut every kUnit positions.  A nominal boundary that falls inside
+// a SHORT segment (<= kUnit positions: almost every row) moves to that segment's end, so the row is owned by
+// exactly one unit and never takes the RED + ticket path; inside a LONG segment (the Zipf head) it stays, so
+// a long row is cut at every multiple of kUnit.  Unit k is therefore a sub-range of the positions
+// [k*kUnit, k*kUnit + kTile): its records sit at a STATIC address (no cut table, no dependent load) and its
+// two ends follow from the records at tile offsets 0 and kUnit.
+#ifndef BRS_ROWS_UNIT_SHIFT
+#define BRS_ROWS_UNIT_SHIFT 4
+#endif
+constexpr int kUnitShift = BRS_ROWS_UNIT_SHIFT;
+constexpr int kUnit = 1 << kUnitShift;
+constexpr int kTile = 2 * kUnit;  // one record per lane
+static_assert(kTile <= 32, "a tile is copied one record per lane");
+
+__device__ __forceinline__ int snap_cut(int pos, int sb, int se) {
+    if (pos <= sb) return pos;          // already a row boundary
+    if (se - sb <= kUnit) return se;    // short row: all of it goes to the earlier unit
+    return pos;                         // long row: cut here
 }
-// parts of the row whose segment is [sb, se): cuts inside a long segment are the multiples of kSnap
-__device__ __forceinline__ int row_parts(int sb, int se, int lo, int hi) {
-    if (sb >= lo && se <= hi) return 1;  // the whole row is in my unit (the common case)
-    if (se - sb <= kSnap) return 1;      // short rows are never cut
-    return ((se - 1) >> kSnapShift) - (sb >> kSnapShift) + 1;
+// parts of the row whose segment is [sb, se)
+__device__ __forceinline__ int row_parts(int sb, int se) {
+    if (se - sb <= kUnit) return 1;
+    return ((se - 1) >> kUnitShift) - (sb >> kUnitShift) + 1;
 }
 
 // ---------------------------------------------------------------------------
@@ -354,16 +370,7 @@ struct RowTable {
     float* g;   // row-major [capacity][D] partial sums of multi-part rows (zero between steps)
 };
 
-#ifdef BRS_ROWS_PROFILE
-#define BRS_PROF_T(x) const long long x = clock64()
-#define BRS_PROF_ADD(k, t0, t1) prof[k] += (t1) - (t0)
-#else
-#define BRS_PROF_T(x)
-#define BRS_PROF_ADD(k, t0, t1)
-#endif
-
 struct RowArgs {
-    long long* prof;  // BRS_ROWS_PROFILE builds: [warps][8] cycle counters
     RowTable ue, ub, ie, ib;  // user emb / user bias / item emb / item bias
     const float* global_bias;
     float* user_stage;        // [user capacity, D] PRE-step rows of the batch's users
@@ -376,7 +383,6 @@ struct RowArgs {
     brs_step_ws* ws;
     OptParams opt;
     int dim;
-    int unit_shift;  // must equal the one the plan's cuts were computed with
     float reg_w, inv_b;
     int release;   // release the rows' slots (0 when a dense sweep still needs the slot maps)
     // items kernel, last block
@@ -390,61 +396,55 @@ struct RowArgs {
 __device__ __forceinline__ float4 ld4(const float* p) { return *(const float4*)p; }
 __device__ __forceinline__ void st4(float* p, float4 v) { *(float4*)p = v; }
 __device__ __forceinline__ float4 ld4_cg(const float* p) { return __ldcg((const float4*)p); }
+__device__ __forceinline__ float4 lds4(const unsigned char* p) { return *(const float4*)p; }
 
-template <int LPR>
-__device__ __forceinline__ float gsum(unsigned gmask, float v) {
-#pragma unroll
-    for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(gmask, v, o);
-    return v;
-}
-
-// A row's last sample (inside this group's range) was accumulated: rows with several parts combine their
-// partial sums through the scratch and the last part to arrive continues; then the optimizer is applied
-// to the row and its bias, the PRE-step row is staged (users) and the slot is released.
-// Group-uniform control flow; only lanes of `gmask` take part.
-template <int LPR, int VPL, bool FULL, int KIND>
+// The last sample of a row part was accumulated by this warp (lane l holds columns 4*(v*32 + l) .. +3):
+// rows with several parts combine their partial sums through the scratch and the last part to arrive
+// continues; then the optimizer is applied to the row and its bias, the PRE-step row is staged (users) and
+// the slot is released.  Warp-uniform control flow.
+template <int VPL, bool FULL, int KIND>
 __device__ __forceinline__ void flush_row(const RowTable& te, const RowTable& tb, int* ticket, int* slot_map,
-                                          float* stage, unsigned gmask, int gl, int lane_base, int D, bool skip,
-                                          int release, const OptScalars& os, int slot, int row, int nparts,
+                                          float* stage, int lane, int D, bool skip, int release,
+                                          const OptScalars& os, int slot, int row, int nparts,
                                           const float4 (&w)[VPL], float4 (&acc)[VPL], float bias, float gbias) {
     const size_t so = (size_t)(unsigned)slot * (unsigned)D;
     if (nparts > 1) {
         if (!skip) {
 #pragma unroll
             for (int v = 0; v < VPL; ++v) {
-                const int col = (v * LPR + gl) * 4;
+                const int col = (v * 32 + lane) * 4;
                 if (FULL || col < D) red_add4(te.g + so + col, acc[v]);
             }
-            if (gl == 0) red_add1(tb.g + slot, gbias);
+            if (lane == 0) red_add1(tb.g + slot, gbias);
             __threadfence();
         }
-        __syncwarp(gmask);
+        __syncwarp();
         int tk = 0;
-        if (gl == 0) tk = atomicAdd(ticket + slot, 1);
-        tk = __shfl_sync(gmask, tk, lane_base);
+        if (lane == 0) tk = atomicAdd(ticket + slot, 1);
+        tk = __shfl_sync(BRS_FULL_MASK, tk, 0);
         if (tk != nparts - 1) return;  // somebody else finishes this row
         __threadfence();
         if (!skip) {
 #pragma unroll
             for (int v = 0; v < VPL; ++v) {
-                const int col = (v * LPR + gl) * 4;
+                const int col = (v * 32 + lane) * 4;
                 if (FULL || col < D) {
                     acc[v] = ld4_cg(te.g + so + col);
                     st4(te.g + so + col, f4_zero());
                 }
             }
-            if (gl == 0) {
+            if (lane == 0) {
                 gbias = __ldcg(tb.g + slot);
                 tb.g[slot] = 0.f;
             }
         }
-        if (gl == 0) ticket[slot] = 0;
+        if (lane == 0) ticket[slot] = 0;
     }
     if (!skip) {
         const size_t ro = (size_t)(unsigned)row * (unsigned)D;
 #pragma unroll
         for (int v = 0; v < VPL; ++v) {
-            const int col = (v * LPR + gl) * 4;
+            const int col = (v * 32 + lane) * 4;
             if (FULL || col < D) {
                 if (stage) st4(stage + so + col, w[v]);  // PRE-step copy for the items kernel
                 float4 mv = f4_zero(), vv = f4_zero();
@@ -457,7 +457,7 @@ __device__ __forceinline__ void flush_row(const RowTable& te, const RowTable& tb
                 if (KIND != BRS_SGD) st4(te.v + ro + col, vv);
             }
         }
-        if (gl == 0) {
+        if (lane == 0) {
             float mb = (KIND == BRS_ADAM) ? tb.m[row] : 0.f;
             float vb = (KIND != BRS_SGD) ? tb.v[row] : 0.f;
             opt_elem<KIND>(bias, gbias, mb, vb, os);
@@ -466,150 +466,95 @@ __device__ __forceinline__ void flush_row(const RowTable& te, const RowTable& tb
             if (KIND != BRS_SGD) tb.v[row] = vb;
         }
     }
-    if (release && gl == 0) slot_map[row] = BRS_SLOT_NONE;
+    if (release && lane == 0) slot_map[row] = BRS_SLOT_NONE;
 }
 
-// Ampere-style asynchronous copies (SASS: LDGSTS) global -> shared, tracked by commit groups.  They are
-// what keeps several samples per lane group in flight without holding them in registers; every lane
-// later reads back exactly the bytes it copied, so no barrier is needed, only cp.async.wait_group.
-// src_bytes == 0 zero-fills the destination (predicated-off lanes / columns past dim).
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(src_bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc, int src_bytes) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(src_bytes)
-                 : "memory");
-}
+// Ampere-style asynchronous copies (SASS: LDGSTS) global -> shared, tracked by commit groups: at dim 128 one
+// warp instruction moves one 512-byte row, and nothing is held in registers while it flies.  Every lane
+// later reads back exactly the row / bias bytes it copied itself, so cp.async.wait_group is all the
+// synchronisation the rows need; record tiles (read by every lane) add one __syncwarp per block.
+// src_bytes == 0 zero-fills the destination (columns past dim / records past the stream end).
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-template <int N>
-struct WaitGroups {
-    static __device__ __forceinline__ void upto(int pending) {  // wait until at most `pending` (< N) groups are in flight
-        if (pending >= N - 1) cp_async_wait<N - 1>();
-        else WaitGroups<N - 1>::upto(pending);
-    }
-};
-template <>
-struct WaitGroups<1> {
-    static __device__ __forceinline__ void upto(int) { cp_async_wait<0>(); }
-};
-
-// shared-memory footprint of one warp: two record tiles per lane group (current / next work unit) + a ring of
-// S stages; a stage holds, for ONE position of every group, NR rows (VPL x 16 bytes per lane) + 4 scalars
-template <int LPR, int VPL, int S, int NR>
-struct RingGeom {
-    static constexpr int SPW = 32 / LPR;
-    static constexpr int TR = 16;  // records (32 bytes each) per group tile >= unit length (L + kSnap - 1, L <= 8)
-    static constexpr int ROW_B = VPL * 512;
-    static constexpr int STAGE_B = NR * ROW_B + SPW * 16;
-    static constexpr int REC_BYTES = 2 * SPW * TR * 32;
-    static constexpr int WARP_B = REC_BYTES + S * STAGE_B;
-};
-
-// Walks a stream for one warp.  Work units are handed out by an atomic counter (one warp-unit = SPW
-// consecutive units, one per lane group), the next unit's records are loaded while the current one is
-// processed, and the rows of up to S positions (the one being consumed included) are in flight in the ring
-// across unit boundaries.  All loop control is warp-uniform; the per-group range lives in lo/nt.
-//   load_rec(buf, t, pos)   record of stream position pos -> slot t of record tile `buf`
-//   issue(buf, t, nt, lo, stage)    start the asynchronous copies of slot t (no-op for t >= nt); NO commit
-//   consume(buf, t, nt, lo, stage)  process slot t (masked for t >= nt)
-template <int LPR, int S, int TR, class LoadRec, class Issue, class Consume>
-__device__ __forceinline__ void walk_stream(int n, int unit_shift, const int* __restrict__ cuts, int* counter, int lane,
-                                            LoadRec load_rec, Issue issue, Consume consume) {
-    constexpr int SPW = 32 / LPR;
-    const int gl = lane % LPR, grp = lane / LPR;
-    const int L = 1 << unit_shift;
-    const int units = (n + L - 1) >> unit_shift;
-    const int warp_units = (units + SPW - 1) / SPW;
-    auto fetch = [&]() {
-        int u = 0;
-        if (lane == 0) u = atomicAdd(counter, 1);
-        return __shfl_sync(BRS_FULL_MASK, u, 0);
-    };
-    auto warp_max = [&](int v) {
+// Sum over the 32 lanes of NV per-lane values with NV - 1 + log2(32 / NV) shuffles instead of 5 * NV: each
+// halving step exchanges half of the values a lane still carries.  Afterwards lane l holds the complete sum
+// of value (l >> (5 - log2 NV)) & (NV - 1)  (NV = 8: index (l >> 2) & 7; NV = 4: index l >> 3).
+template <int NV>
+__device__ __forceinline__ float transpose_reduce(float (&v)[NV], int lane) {
+    int o = 16;
 #pragma unroll
-        for (int o = LPR; o < 32; o <<= 1) v = max(v, __shfl_xor_sync(BRS_FULL_MASK, v, o));
-        return v;
-    };
-    // range of this group in warp-unit wu + its records into tile `buf`
-    auto setup = [&](int wu, int buf, int& lo, int& nt) {
-        lo = 0;
-        nt = 0;
-        const int k = wu * SPW + grp;
-        if (wu < warp_units && k < units) {
-            lo = __ldg(cuts + k);
-            nt = min(TR, max(0, __ldg(cuts + k + 1) - lo));
+    for (int n = NV; n > 1; n >>= 1) {
+        const bool hi = (lane & o) != 0;
+#pragma unroll
+        for (int k = 0; k < n / 2; ++k) {
+            const float keep = hi ? v[k + n / 2] : v[k];
+            const float send = hi ? v[k] : v[k + n / 2];
+            v[k] = keep + __shfl_xor_sync(BRS_FULL_MASK, send, o);
         }
-        for (int t = gl; t < nt; t += LPR) load_rec(buf, t, lo + t);
-    };
-    int wu_c = fetch(), lo_c, nt_c, lo_n, nt_n;
-    if (wu_c >= warp_units) return;  // warp-uniform
-    setup(wu_c, 0, lo_c, nt_c);
-    int wu_n = fetch();
-    setup(wu_n, 1, lo_n, nt_n);
-    int ntw_c = warp_max(nt_c), ntw_n = warp_max(nt_n);
-    int cb = 0;               // record tile of the current unit
-    int iu = 0, it = 0;       // issue pointer: unit (0 = current, 1 = next), slot
-    int gi = 0, gc = 0;       // positions issued / consumed so far (ring stage = count % S)
-    __syncwarp();
-    auto advance = [&]() -> bool {  // issue the next position of the concatenated units, if any is known yet
-        if (iu == 0 && it >= ntw_c) {
-            iu = 1;
-            it = 0;
-        }
-        if (iu == 0) issue(cb, it, nt_c, lo_c, gi % S);
-        else if (it < ntw_n) issue(cb ^ 1, it, nt_n, lo_n, gi % S);
-        else return false;
-        cp_async_commit();
-        ++it;
-        ++gi;
-        return true;
-    };
-    while (wu_c < warp_units) {  // warp-uniform
-        for (int t = 0; t < ntw_c; ++t) {
-            __syncwarp();  // every lane has finished reading the stage that may be refilled now
-            while (gi - gc < S && advance()) {
-            }
-            WaitGroups<S>::upto(gi - gc - 1);  // position gc has landed (this lane's own copies)
-            __syncwarp();                      // ... and the scalar cells written by other lanes of the group
-            consume(cb, t, nt_c, lo_c, gc % S);
-            ++gc;
-        }
-        __syncwarp();  // the current unit's records are dead: its tile is refilled with the unit after next
-        cb ^= 1;
-        wu_c = wu_n;
-        lo_c = lo_n;
-        nt_c = nt_n;
-        ntw_c = ntw_n;
-        if (iu == 1) iu = 0;  // `it` positions of the new current unit are already in flight
-        else it = 0;
-        wu_n = wu_c < warp_units ? fetch() : warp_units;
-        setup(wu_n, cb ^ 1, lo_n, nt_n);
-        ntw_n = warp_max(nt_n);
-        __syncwarp();
+        o >>= 1;
     }
-    cp_async_wait<0>();
+    float r = v[0];
+    for (; o > 0; o >>= 1) r += __shfl_xor_sync(BRS_FULL_MASK, r, o);
+    return r;
 }
 
-template <int LPR, int VPL, bool FULL, int LOSS, int KIND, int S, int NW>
+// A warp's walk over its units: unit number seq of warp gw is unit gw + seq * W of the stream.
+struct UnitGen {
+    int seq;    // units entered so far - 1
+    int slot;   // record tile of the current unit (seq % NT)
+    int base;   // first position the tile covers
+    int lo, hi; // the unit: [lo, hi)
+    int p;      // next position to hand out
+    bool valid;
+};
+
+// geometry of one warp's shared memory: NT record tiles + a ring of NB blocks of KB stages (one per position)
+template <int VPL, int NB, int KB, int NR, int REC_B>
+struct RingGeom {
+    static constexpr int NT = 2 * NB - 1;  // tiles alive: NB - 1 behind the issue pointer, it, NB - 1 prefetched
+    static constexpr int PD = NB - 1;      // tile prefetch distance in units
+    static constexpr int ROW_B = VPL * 512;
+    static constexpr int BIAS_OFF = NR * ROW_B;
+    static constexpr int STAGE_B = NR * ROW_B + 128;  // + one 4-byte cell per lane
+    static constexpr int TILE_B = kTile * REC_B;
+    static constexpr int WARP_B = NT * TILE_B + NB * KB * STAGE_B;
+    static constexpr int CACHE_B = kHotRows * ROW_B;  // per CTA, after the warps' regions
+};
+
+__device__ __forceinline__ void cp_async16_s(uint32_t dst, const void* gsrc, int src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async16_sf(uint32_t dst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async4_s(uint32_t dst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(gsrc) : "memory");
+}
+
+// users kernel: one warp walks units of the user stream, KB positions per block.
+//   issue    per position: pos / neg item rows (+ the user row at the first position of a row part) and the
+//            three biases (lanes 0..2) by cp.async into the block's ring slot
+//   phase 1  per position: per-lane partial dots u.i, u.j (+ the bias a lane copied)
+//   phase 2  ONE transposing reduction for the block's 2*KB dots, then the sigmoid / loss / d loss chain
+//            once per block (lane group k works on position k); (coefficient, user slot) -> item stream
+//   phase 3  per position: gradient of the user row accumulated in registers; at the end of a row part:
+//            regularizer term of the row, PRE-step row -> staging table, updated row -> table
+template <int VPL, bool FULL, int LOSS, int KIND, int NB, int NW, int KB>
 __global__ void __launch_bounds__(NW * 32) mf_user_rows_kernel(const RowArgs a) {
-    constexpr int SPW = 32 / LPR;
     constexpr int C = (LOSS == LOSS_BPR) ? 2 : 1;
-    using G = RingGeom<LPR, VPL, S, 3>;
-    constexpr int TR = G::TR;
+    using G = RingGeom<VPL, NB, KB, 3, 32>;
+    constexpr int NT = G::NT, PD = G::PD;
+    constexpr int KSH = KB == 4 ? 3 : 4;  // lanes [k << KSH, (k + 1) << KSH) run the loss chain of position k
+    static_assert(KB == 2 || KB == 4, "block = 2 or 4 positions");
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ OptScalars s_opt;
     __shared__ float s_red[3][NW];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const int gl = lane % LPR, grp = lane / LPR;
-    const int lane_base = grp * LPR;
-    const unsigned gmask = LPR == 32 ? 0xffffffffu : (((1u << (LPR & 31)) - 1u) << lane_base);
     const int D = a.dim;
     if (threadIdx.x == 0) s_opt = make_scalars(a.opt, a.ws->step + 1);
     __syncthreads();
@@ -619,129 +564,251 @@ __global__ void __launch_bounds__(NW * 32) mf_user_rows_kernel(const RowArgs a) 
     const int n = __ldg(a.pv.hdr + 0);
     const float rw = 2.0f * a.reg_w * a.inv_b;  // d(reg_w*regularizer)/d row = rw * row per forward call
     const float fwd_calls = (float)C;
+    const int W = gridDim.x * NW;
+    const int gw = warp * gridDim.x + blockIdx.x;  // consecutive units run on different SMs
     float loss_acc = 0.f, reg_acc = 0.f, gb_acc = 0.f;
 
     unsigned char* wbase = smem + (size_t)warp * G::WARP_B;
-    // record slot t of the group's tile `buf`: rec[2t] = s_a, rec[2t+1] = s_b
-    auto rec_of = [&](int buf) { return (int4*)wbase + (buf * SPW + grp) * TR * 2; };
-    unsigned char* ring = wbase + G::REC_BYTES;
-    // this lane's 16-byte cells inside a stage: row r, vector v at ((r * VPL + v) * 32 + lane) * 16
+    int4* tiles = (int4*)wbase;  // tile s: records [2t] = s_a, [2t+1] = s_b
+    unsigned char* ring = wbase + NT * G::TILE_B;
+    const uint32_t tiles_s = smem_u32(tiles), ring_s = smem_u32(ring);
     const int cell = lane * 16;
-    const int bcell = 3 * G::ROW_B + grp * 16;  // the group's {b_u, b_i, b_j} of the position
-
-    float4 acc[VPL], ru[VPL];  // the user row being accumulated: gradient, PRE-step weights
-    float gbias = 0.f, bu = 0.f, uu = 0.f;
-    int n_row = 0;
-#pragma unroll
-    for (int v = 0; v < VPL; ++v) acc[v] = ru[v] = f4_zero();
-
-    auto load_rec = [&](int buf, int t, int pos) {
-        int4* rec = rec_of(buf);
-        rec[2 * t] = __ldg(a.pv.s_a + pos);
-        rec[2 * t + 1] = __ldg(a.pv.s_b + pos);
-    };
-    // asynchronous gather of a position's rows into a ring stage.  The stream is sorted by user, so the
-    // user row (and bias) only travels with the FIRST sample of a row inside the unit
-    auto issue = [&](int buf, int t, int nt, int lo, int stage) {
-        if (t >= nt) return;
-        const int4* rec = rec_of(buf);
-        unsigned char* st = ring + stage * G::STAGE_B;
-        const int4 ra = rec[2 * t];
-        const bool first = lo + t == rec[2 * t + 1].z || t == 0;
-        const float* up = a.ue.w + (size_t)(unsigned)ra.x * (unsigned)D;
-        const float* ip = a.ie.w + (size_t)(unsigned)ra.z * (unsigned)D;
-        const float* jp = a.ie.w + (size_t)(unsigned)(C == 2 ? ra.w : 0) * (unsigned)D;
-#pragma unroll
-        for (int v = 0; v < VPL; ++v) {
-            const int col = (v * LPR + gl) * 4;
-            const bool ld = FULL || col < D;
-            const int cc = ld ? col : 0;
-            unsigned char* d0 = st + v * 512 + cell;
-            if (first) cp_async16(d0, up + cc, ld ? 16 : 0);
-            cp_async16(d0 + G::ROW_B, ip + cc, ld ? 16 : 0);
-            if (C == 2) cp_async16(d0 + 2 * G::ROW_B, jp + cc, ld ? 16 : 0);
-        }
-        // lanes 0..2 of the group fetch the three biases (they wrap around for tiny dims)
-#pragma unroll
-        for (int k = gl; k < 1 + C; k += LPR) {
-            const float* bp = k == 0 ? a.ub.w + (unsigned)ra.x : (k == 1 ? a.ib.w + (unsigned)ra.z : a.ib.w + (unsigned)ra.w);
-            if (k != 0 || first) cp_async4(st + bcell + k * 4, bp, 4);
-        }
-    };
-    auto consume = [&](int buf, int t, int nt, int lo, int stage) {
-        const bool on = t < nt;  // groups past their unit compute on stale data, side effects are masked
-        const int tc = on ? t : 0;
-        const int4* rec = rec_of(buf);
-        const unsigned char* st = ring + stage * G::STAGE_B;
-        const int4 ra = rec[2 * tc], rb = rec[2 * tc + 1];
-        const int p = lo + tc, hi = lo + nt;
-        const int slot = ra.y, sb = rb.z, se = rb.w;
-        const bool first = on && (p == sb || tc == 0);
-        const float4 bb = *(const float4*)(st + bcell);  // {b_u, b_i, b_j, -}
-        if (first) {  // a new user row starts here: its PRE-step weights stay in registers
-            uu = 0.f;
+    const int bcell = G::BIAS_OFF + lane * 4;
+    // per-lane constants of the gathers: column of vector v, its validity, the lane's bias table
+    const float* ue_l = a.ue.w + lane * 4;
+    const float* ie_l = a.ie.w + lane * 4;
+    const float* btab = lane == 0 ? a.ub.w : a.ib.w;
+    const bool bias_lane = lane <= C;
+    // the batch's hot item rows (PRE-step: this kernel never writes item rows) -> shared memory, once per CTA
+    const unsigned char* cache = smem + NW * G::WARP_B;
+    {
+        const int nh = min(__ldg(a.pv.hdr + 5), kHotRows);
+        for (int h = warp; h < nh; h += NW) {
+            const float* src = ie_l + (size_t)(unsigned)__ldg(a.pv.i_hotlist + h) * (unsigned)D;
 #pragma unroll
             for (int v = 0; v < VPL; ++v) {
-                ru[v] = *(const float4*)(st + v * 512 + cell);
-                uu += f4_dot(ru[v], ru[v]);
-                acc[v] = f4_zero();
-            }
-            bu = bb.x;
-            gbias = 0.f;
-            n_row = 0;
-        }
-        float4 ri[VPL], rj[C == 2 ? VPL : 1];
-        float dp = 0.f, dn = 0.f, sq = 0.f;
-#pragma unroll
-        for (int v = 0; v < VPL; ++v) {
-            const unsigned char* d0 = st + v * 512 + cell;
-            ri[v] = *(const float4*)(d0 + G::ROW_B);
-            dp += f4_dot(ru[v], ri[v]);
-            sq += f4_dot(ri[v], ri[v]);
-            if (C == 2) {
-                rj[v] = *(const float4*)(d0 + 2 * G::ROW_B);
-                dn += f4_dot(ru[v], rj[v]);
-                sq += f4_dot(rj[v], rj[v]);
+                const bool ld = FULL || (v * 32 + lane) * 4 < D;
+                *(float4*)(smem + NW * G::WARP_B + h * G::ROW_B + v * 512 + cell) = ld ? ld4(src + v * 128) : f4_zero();
             }
         }
-        const float bi = bb.y, bj = (C == 2) ? bb.z : 0.f;
-        dp = group_sum<LPR>(dp);
-        if (C == 2) dn = group_sum<LPR>(dn);
-        const float rating = (C == 1) ? __int_as_float(ra.w) : 0.f;
-        float cu_i, cu_j, loss_k;
-        mf_sample_coef<LOSS>(dp + bu + bi + bg, dn + bu + bj + bg, rating, a.inv_b, cu_i, cu_j, loss_k);
-        if (!on) return;
-        reg_acc += fwd_calls * uu + sq;  // regularizer numerator (mf.py:49-54)
-        if (gl == 0) {
-            reg_acc += fwd_calls * bu * bu + bi * bi + bj * bj;
-            loss_acc += loss_k;
-            gb_acc += cu_i + cu_j;
-            const float sf = __int_as_float(slot);  // hand the coefficients to the item stream
-            a.pv.ipair[rb.x] = make_float2(cu_i, sf);
-            if (C == 2) a.pv.ipair[rb.y] = make_float2(cu_j, sf);
-        }
-#pragma unroll
-        for (int v = 0; v < VPL; ++v) {
-            acc[v] = f4_fma(cu_i, ri[v], acc[v]);
-            if (C == 2) acc[v] = f4_fma(cu_j, rj[v], acc[v]);
-        }
-        gbias += cu_i + cu_j;
-        n_row += 1;
-        if (p + 1 == se || p + 1 == hi) {  // last sample of this row inside my unit
-            if (a.reg_w != 0.f) {
-                const float nl = fwd_calls * (float)n_row * rw;
-#pragma unroll
-                for (int v = 0; v < VPL; ++v) acc[v] = f4_fma(nl, ru[v], acc[v]);
-                gbias += nl * bu;
-            }
-            flush_row<LPR, VPL, FULL, KIND>(a.ue, a.ub, a.pv.u_ticket, a.u_slot_map, a.user_stage, gmask, gl, lane_base, D, skip,
-                                            a.release, os, slot, ra.x, row_parts(sb, se, lo, hi), ru, acc, bu, gbias);
+        __syncthreads();
+    }
+
+    auto issue_tile = [&](int seq) {
+        const int pos = ((gw + seq * W) << kUnitShift) + lane;
+        const bool ok = lane < kTile && pos < n;
+        const uint32_t tl = tiles_s + (seq % NT) * G::TILE_B + lane * 32;
+        if (lane < kTile) {
+            cp_async16_s(tl, a.pv.s_a + (ok ? pos : 0), ok ? 16 : 0);
+            cp_async16_s(tl + 16, a.pv.s_b + (ok ? pos : 0), ok ? 16 : 0);
         }
     };
-    walk_stream<LPR, S, TR>(n, a.unit_shift, a.pv.u_cuts, a.pv.hdr + 2, lane, load_rec, issue, consume);
+    auto enter = [&](UnitGen& g, bool prefetch) {  // move on to the warp's next non-empty unit
+        for (;;) {
+            g.seq += 1;
+            g.slot = g.slot + 1 == NT ? 0 : g.slot + 1;
+            if (prefetch) issue_tile(g.seq + PD);
+            const int base = (gw + g.seq * W) << kUnitShift;
+            if (base >= n) {
+                g.valid = false;
+                return;
+            }
+            const int4* tl = tiles + g.slot * (kTile * 2);
+            const int4 r0 = tl[1], r1 = tl[2 * kUnit + 1];
+            g.base = base;
+            g.lo = snap_cut(base, r0.z, r0.w);
+            g.hi = base + kUnit >= n ? n : snap_cut(base + kUnit, r1.z, r1.w);
+            g.p = g.lo;
+            if (g.lo < g.hi) return;
+        }
+    };
+    auto issue_block = [&](UnitGen& g, int rslot) {
+        if (g.valid && g.p >= g.hi) enter(g, true);
+        if (!g.valid) return;
+        const int cnt = min(KB, g.hi - g.p);
+        const int4* tl = tiles + g.slot * (kTile * 2) + 2 * (g.p - g.base);
+        const uint32_t st0 = ring_s + rslot * (KB * G::STAGE_B) + cell;
+#pragma unroll
+        for (int k = 0; k < KB; ++k) {
+            if (k < cnt) {  // warp-uniform
+                const int4 ra = tl[2 * k];
+                const int4 rb = tl[2 * k + 1];
+                const bool first = g.p + k == rb.z || g.p + k == g.lo;  // the user row travels with the first position of a part
+                const bool gi_ = (rb.x >> kPosBits) == 0;               // hot item rows are read from the CTA's cache instead
+                const bool gj_ = C == 2 && (rb.y >> kPosBits) == 0;
+                const uint32_t st = st0 + k * G::STAGE_B;
+                const float* up = ue_l + (size_t)(unsigned)ra.x * (unsigned)D;
+                const float* ip = ie_l + (size_t)(unsigned)ra.z * (unsigned)D;
+                const float* jp = ie_l + (size_t)(unsigned)(C == 2 ? ra.w : 0) * (unsigned)D;
+#pragma unroll
+                for (int v = 0; v < VPL; ++v) {
+                    if (FULL) {
+                        if (first) cp_async16_sf(st + v * 512, up + v * 128);
+                        if (gi_) cp_async16_sf(st + v * 512 + G::ROW_B, ip + v * 128);
+                        if (gj_) cp_async16_sf(st + v * 512 + 2 * G::ROW_B, jp + v * 128);
+                    } else {
+                        const bool ld = (v * 32 + lane) * 4 < D;
+                        const int cc = ld ? v * 128 : -lane * 4;
+                        if (first) cp_async16_s(st + v * 512, up + cc, ld ? 16 : 0);
+                        if (gi_) cp_async16_s(st + v * 512 + G::ROW_B, ip + cc, ld ? 16 : 0);
+                        if (gj_) cp_async16_s(st + v * 512 + 2 * G::ROW_B, jp + cc, ld ? 16 : 0);
+                    }
+                }
+                // lane 0: user bias, lane 1: pos-item bias, lane 2: neg-item bias -- into the lane's own cell
+                const int bi_ = lane == 0 ? ra.x : (lane == 1 ? ra.z : ra.w);
+                if (lane == 0 ? first : bias_lane) cp_async4_s(st - cell + bcell, btab + (unsigned)bi_);
+            }
+        }
+        g.p += cnt;
+    };
+
+    // state of the row part being accumulated (phase 3) -- carried across blocks, never across units
+    float4 ru[VPL], acc[VPL];
+    float uu = 0.f, bu = 0.f, gbias = 0.f;
+    int n_row = 0;
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) ru[v] = acc[v] = f4_zero();
+
+    auto consume = [&](const UnitGen& g, int p0, int cnt, int rslot) {
+        const int4* tl = tiles + g.slot * (kTile * 2) + 2 * (p0 - g.base);  // record of block position k: tl[2k], tl[2k+1]
+        const unsigned char* blk = ring + rslot * (KB * G::STAGE_B);
+        // ---- phase 1: partial dots of the block's positions
+        float dots[KB * C];
+        {
+            float4 r1[VPL];
+            float bu1 = bu;
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) r1[v] = ru[v];
+#pragma unroll
+            for (int k = 0; k < KB; ++k) {
+                const bool on = k < cnt;  // positions past the block's end compute on stale data, nothing is kept
+                const int kk = on ? k : 0;
+                const int4 rb = tl[2 * kk + 1];
+                const bool first = on && (p0 + k == rb.z || p0 + k == g.lo);
+                const unsigned char* st = blk + k * G::STAGE_B;
+                const int hi_ = rb.x >> kPosBits, hj_ = C == 2 ? rb.y >> kPosBits : 0;
+                const unsigned char* irow = (hi_ ? cache + (hi_ - 1) * G::ROW_B : st + G::ROW_B) + cell;
+                const unsigned char* jrow = (hj_ ? cache + (hj_ - 1) * G::ROW_B : st + 2 * G::ROW_B) + cell;
+                const float b = *(const float*)(st + bcell);
+                if (first) {
+#pragma unroll
+                    for (int v = 0; v < VPL; ++v) r1[v] = lds4(st + v * 512 + cell);
+                    bu1 = b;  // meaningful on lane 0 only
+                }
+                float dp = 0.f, dn = 0.f;
+#pragma unroll
+                for (int v = 0; v < VPL; ++v) {
+                    dp += f4_dot(r1[v], lds4(irow + v * 512));
+                    if (C == 2) dn += f4_dot(r1[v], lds4(jrow + v * 512));
+                }
+                // every bias enters the score through the lane that copied it
+                const float ub_ = bu1 + bg;
+                dots[C * k] = dp + (lane == 0 ? ub_ : (lane == 1 ? b : 0.f));
+                if (C == 2) dots[C * k + 1] = dn + (lane == 0 ? ub_ : (lane == 2 ? b : 0.f));
+            }
+        }
+        // ---- phase 2: one reduction, one loss chain per block; lanes [k << KSH, (k+1) << KSH) work on position k
+        float z = transpose_reduce<KB * C>(dots, lane);
+        float zp = z, zn = 0.f;
+        if (C == 2) {
+            const float other = __shfl_xor_sync(BRS_FULL_MASK, z, 1 << (KSH - 1));
+            const bool odd = (lane & (1 << (KSH - 1))) != 0;
+            zp = odd ? other : z;
+            zn = odd ? z : other;
+        }
+        const int kl = lane >> KSH;
+        const bool onl = kl < cnt;
+        const int4 la = tl[2 * (onl ? kl : 0)], lb = tl[2 * (onl ? kl : 0) + 1];
+        const float rating = (C == 1) ? __int_as_float(la.w) : 0.f;
+        float cu_i, cu_j, loss_k;
+        mf_sample_coef_fast<LOSS>(zp, zn, rating, a.inv_b, cu_i, cu_j, loss_k);
+        if (onl && (lane & ((1 << KSH) - 1)) == 0) {
+            loss_acc += loss_k;
+            gb_acc += cu_i + cu_j;
+            const float sf = __int_as_float(la.y);  // hand the coefficients (+ user slot | hot index) to the item stream
+            a.pv.ipair[lb.x & ((1 << kPosBits) - 1)] = make_float2(cu_i, sf);
+            if (C == 2) a.pv.ipair[lb.y & ((1 << kPosBits) - 1)] = make_float2(cu_j, sf);
+        }
+        // ---- phase 3: gradient of the user row
+#pragma unroll
+        for (int k = 0; k < KB; ++k) {
+            if (k < cnt) {  // warp-uniform
+                const float ci = __shfl_sync(BRS_FULL_MASK, cu_i, k << KSH);
+                const float cj = (C == 2) ? __shfl_sync(BRS_FULL_MASK, cu_j, k << KSH) : 0.f;
+                const int p = p0 + k;
+                const int4 rb = tl[2 * k + 1];
+                const unsigned char* st = blk + k * G::STAGE_B;
+                const int hi_ = rb.x >> kPosBits, hj_ = C == 2 ? rb.y >> kPosBits : 0;
+                const unsigned char* irow = (hi_ ? cache + (hi_ - 1) * G::ROW_B : st + G::ROW_B) + cell;
+                const unsigned char* jrow = (hj_ ? cache + (hj_ - 1) * G::ROW_B : st + 2 * G::ROW_B) + cell;
+                if (p == rb.z || p == g.lo) {  // a new row part starts here: its PRE-step weights stay in registers
+                    uu = 0.f;
+#pragma unroll
+                    for (int v = 0; v < VPL; ++v) {
+                        ru[v] = lds4(st + v * 512 + cell);
+                        uu += f4_dot(ru[v], ru[v]);
+                        acc[v] = f4_zero();
+                    }
+                    bu = *(const float*)(st + bcell);
+                    gbias = 0.f;
+                    n_row = 0;
+                }
+#pragma unroll
+                for (int v = 0; v < VPL; ++v) {
+                    acc[v] = f4_fma(ci, lds4(irow + v * 512), acc[v]);
+                    if (C == 2) acc[v] = f4_fma(cj, lds4(jrow + v * 512), acc[v]);
+                }
+                gbias += ci + cj;
+                n_row += 1;
+                if (p + 1 == rb.w || p + 1 == g.hi) {  // last sample of this row inside my unit
+                    const int4 ra = tl[2 * k];
+                    // regularizer numerator (mf.py:49-54): every forward call of every sample adds |u|^2 + b_u^2
+                    reg_acc += fwd_calls * (float)n_row * (uu + (lane == 0 ? bu * bu : 0.f));
+                    if (a.reg_w != 0.f) {
+                        const float nl = fwd_calls * (float)n_row * rw;
+#pragma unroll
+                        for (int v = 0; v < VPL; ++v) acc[v] = f4_fma(nl, ru[v], acc[v]);
+                        gbias += nl * bu;
+                    }
+                    flush_row<VPL, FULL, KIND>(a.ue, a.ub, a.pv.u_ticket, a.u_slot_map, a.user_stage, lane, D, skip, a.release,
+                                               os, ra.y & ((1 << kSlotBits) - 1), ra.x, row_parts(rb.z, rb.w), ru, acc, bu, gbias);
+                }
+            }
+        }
+    };
+
+    // ---- the walk: the issue pointer runs NB - 1 blocks ahead of the consume pointer, across units
+    UnitGen gi, gc;
+    gi.seq = gc.seq = -1;
+    gi.slot = gc.slot = NT - 1;
+    gi.base = gc.base = gi.lo = gc.lo = gi.hi = gc.hi = gi.p = gc.p = 0;
+    gi.valid = gc.valid = true;
+    for (int s = 0; s < PD; ++s) issue_tile(s);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncwarp();
+    for (int b = 0; b < NB - 1; ++b) {
+        issue_block(gi, b);
+        cp_async_commit();
+    }
+    int cslot = 0, islot = NB - 1;
+    for (;;) {
+        cp_async_wait<NB - 2>();  // the block about to be consumed has landed (this lane's own copies) ...
+        __syncwarp();             // ... and so have the record tiles copied by other lanes; the ring slot
+                                  // consumed last round may be refilled
+        issue_block(gi, islot);
+        cp_async_commit();
+        if (gc.valid && gc.p >= gc.hi) enter(gc, false);
+        if (!gc.valid) break;
+        const int p0 = gc.p, cnt = min(KB, gc.hi - gc.p);
+        gc.p += cnt;
+        consume(gc, p0, cnt, cslot);
+        cslot = cslot + 1 == NB ? 0 : cslot + 1;
+        islot = islot + 1 == NB ? 0 : islot + 1;
+    }
+    cp_async_wait<0>();
 
     // block reduction of the scalar outputs -> 3 atomics per block
-    __syncwarp();
     loss_acc = warp_sum(loss_acc);
     reg_acc = warp_sum(reg_acc);
     gb_acc = warp_sum(gb_acc);
@@ -767,19 +834,20 @@ __global__ void __launch_bounds__(NW * 32) mf_user_rows_kernel(const RowArgs a) 
     }
 }
 
-template <int LPR, int VPL, bool FULL, int KIND, int S, int NW>
+// items kernel: the same walk over the item stream.  Every entry brings the staged PRE-step row of its
+// user; the item's own row (and bias) only travels with the LAST entry of a row part, where the update is
+// applied (and the row's regularizer term is taken).  The last block to finish applies the global-bias
+// step and publishes brs_step_out.
+template <int VPL, bool FULL, int KIND, int NB, int NW, int KB>
 __global__ void __launch_bounds__(NW * 32) mf_item_rows_kernel(const RowArgs a) {
-    constexpr int SPW = 32 / LPR;
-    using G = RingGeom<LPR, VPL, S, 2>;
-    constexpr int TR = G::TR;
+    using G = RingGeom<VPL, NB, KB, 2, 24>;
+    constexpr int NT = G::NT, PD = G::PD;
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ OptScalars s_opt;
+    __shared__ float s_red[NW];
     __shared__ bool s_last;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const int gl = lane % LPR, grp = lane / LPR;
-    const int lane_base = grp * LPR;
-    const unsigned gmask = LPR == 32 ? 0xffffffffu : (((1u << (LPR & 31)) - 1u) << lane_base);
     const int D = a.dim;
     if (threadIdx.x == 0) s_opt = make_scalars(a.opt, a.ws->step + 1);
     __syncthreads();
@@ -787,13 +855,101 @@ __global__ void __launch_bounds__(NW * 32) mf_item_rows_kernel(const RowArgs a) 
     const bool skip = __ldg(a.err) != 0u;
     const int n = __ldg(a.pv.hdr + 1);
     const float rw = 2.0f * a.reg_w * a.inv_b;
+    const int W = gridDim.x * NW;
+    const int gw = warp * gridDim.x + blockIdx.x;
+    float reg_acc = 0.f;
 
     unsigned char* wbase = smem + (size_t)warp * G::WARP_B;
-    // entry slot t of the group's tile `buf`: rec[2t] = i_a, rec[2t+1].xy = ipair {coefficient, user slot}
-    auto rec_of = [&](int buf) { return (int4*)wbase + (buf * SPW + grp) * TR * 2; };
-    unsigned char* ring = wbase + G::REC_BYTES;
+    // tile s: kTile records i_a (16 bytes each), then kTile pairs {coefficient, user slot} (8 bytes each)
+    auto tile_a = [&](int slot) { return (const int4*)(wbase + slot * G::TILE_B); };
+    auto tile_p = [&](int slot) { return (const float2*)(wbase + slot * G::TILE_B + kTile * 16); };
+    unsigned char* ring = wbase + NT * G::TILE_B;
+    const uint32_t tiles_s = smem_u32(wbase), ring_s = smem_u32(ring);
     const int cell = lane * 16;
-    const int bcell = 2 * G::ROW_B + grp * 16;
+    const int bcell = G::BIAS_OFF;  // lane 0's cell
+    const float* us_l = a.user_stage + lane * 4;
+    const float* ie_l = a.ie.w + lane * 4;
+    // the staged PRE-step rows of the batch's hot users -> shared memory, once per CTA
+    const unsigned char* cache = smem + NW * G::WARP_B;
+    {
+        const int nh = min(__ldg(a.pv.hdr + 4), kHotRows);
+        for (int h = warp; h < nh; h += NW) {
+            const float* src = us_l + (size_t)(unsigned)__ldg(a.pv.u_hotlist + h) * (unsigned)D;
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) {
+                const bool ld = FULL || (v * 32 + lane) * 4 < D;
+                *(float4*)(smem + NW * G::WARP_B + h * G::ROW_B + v * 512 + cell) = ld ? ld4(src + v * 128) : f4_zero();
+            }
+        }
+        __syncthreads();
+    }
+
+    auto issue_tile = [&](int seq) {
+        const int pos = ((gw + seq * W) << kUnitShift) + lane;
+        const bool ok = lane < kTile && pos < n;
+        const uint32_t tl = tiles_s + (seq % NT) * G::TILE_B;
+        if (lane < kTile) {
+            cp_async16_s(tl + lane * 16, a.pv.i_a + (ok ? pos : 0), ok ? 16 : 0);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(tl + kTile * 16 + lane * 8),
+                         "l"(a.pv.ipair + (ok ? pos : 0)), "r"(ok ? 8 : 0)
+                         : "memory");
+        }
+    };
+    auto enter = [&](UnitGen& g, bool prefetch) {
+        for (;;) {
+            g.seq += 1;
+            g.slot = g.slot + 1 == NT ? 0 : g.slot + 1;
+            if (prefetch) issue_tile(g.seq + PD);
+            const int base = (gw + g.seq * W) << kUnitShift;
+            if (base >= n) {
+                g.valid = false;
+                return;
+            }
+            const int4* tl = tile_a(g.slot);
+            const int4 r0 = tl[0], r1 = tl[kUnit];
+            g.base = base;
+            g.lo = snap_cut(base, r0.z, r0.w);
+            g.hi = base + kUnit >= n ? n : snap_cut(base + kUnit, r1.z, r1.w);
+            g.p = g.lo;
+            if (g.lo < g.hi) return;
+        }
+    };
+    auto issue_block = [&](UnitGen& g, int rslot) {
+        if (g.valid && g.p >= g.hi) enter(g, true);
+        if (!g.valid) return;
+        const int cnt = min(KB, g.hi - g.p);
+        const int4* ta = tile_a(g.slot) + (g.p - g.base);
+        const float2* tp = tile_p(g.slot) + (g.p - g.base);
+        const uint32_t st0 = ring_s + rslot * (KB * G::STAGE_B) + cell;
+#pragma unroll
+        for (int k = 0; k < KB; ++k) {
+            if (k < cnt) {  // warp-uniform
+                const int q = g.p + k;
+                const int4 ia = ta[k];
+                const int usy = __float_as_int(tp[k].y);
+                const int us = usy & ((1 << kSlotBits) - 1);
+                const bool gu_ = (usy >> kSlotBits) == 0;  // hot users' rows are read from the CTA's cache instead
+                const bool last = q + 1 == ia.w || q + 1 == g.hi;
+                const uint32_t st = st0 + k * G::STAGE_B;
+                const float* up = us_l + (size_t)(unsigned)us * (unsigned)D;
+                const float* ip = ie_l + (size_t)(unsigned)ia.x * (unsigned)D;
+#pragma unroll
+                for (int v = 0; v < VPL; ++v) {
+                    if (FULL) {
+                        if (gu_) cp_async16_sf(st + v * 512, up + v * 128);
+                        if (last) cp_async16_sf(st + v * 512 + G::ROW_B, ip + v * 128);
+                    } else {
+                        const bool ld = (v * 32 + lane) * 4 < D;
+                        const int cc = ld ? v * 128 : -lane * 4;
+                        if (gu_) cp_async16_s(st + v * 512, up + cc, ld ? 16 : 0);
+                        if (last) cp_async16_s(st + v * 512 + G::ROW_B, ip + cc, ld ? 16 : 0);
+                    }
+                }
+                if (last && lane == 0) cp_async4_s(st + bcell, a.ib.w + (unsigned)ia.x);
+            }
+        }
+        g.p += cnt;
+    };
 
     float4 acc[VPL];
     float gbias = 0.f;
@@ -801,69 +957,91 @@ __global__ void __launch_bounds__(NW * 32) mf_item_rows_kernel(const RowArgs a) 
 #pragma unroll
     for (int v = 0; v < VPL; ++v) acc[v] = f4_zero();
 
-    auto load_rec = [&](int buf, int t, int pos) {
-        int4* rec = rec_of(buf);
-        rec[2 * t] = __ldg(a.pv.i_a + pos);
-        const float2 pr = __ldcg(a.pv.ipair + pos);
-        rec[2 * t + 1] = make_int4(__float_as_int(pr.x), __float_as_int(pr.y), 0, 0);
-    };
-    // the item's own row (and bias) only travels with the LAST entry of the row inside the unit, where the
-    // update is applied; every entry brings the staged PRE-step row of its user
-    auto issue = [&](int buf, int t, int nt, int lo, int stage) {
-        if (t >= nt) return;
-        const int4* rec = rec_of(buf);
-        unsigned char* st = ring + stage * G::STAGE_B;
-        const int4 ia = rec[2 * t];
-        const int us = rec[2 * t + 1].y;
-        const bool last = lo + t + 1 == ia.w || t + 1 == nt;
-        const float* up = a.user_stage + (size_t)(unsigned)us * (unsigned)D;
-        const float* ip = a.ie.w + (size_t)(unsigned)ia.x * (unsigned)D;
+    auto consume = [&](const UnitGen& g, int q0, int cnt, int rslot) {
+        const int4* ta = tile_a(g.slot) + (q0 - g.base);
+        const float2* tp = tile_p(g.slot) + (q0 - g.base);
+        const unsigned char* blk = ring + rslot * (KB * G::STAGE_B);
 #pragma unroll
-        for (int v = 0; v < VPL; ++v) {
-            const int col = (v * LPR + gl) * 4;
-            const bool ld = FULL || col < D;
-            const int cc = ld ? col : 0;
-            unsigned char* d0 = st + v * 512 + cell;
-            cp_async16(d0, up + cc, ld ? 16 : 0);
-            if (last) cp_async16(d0 + G::ROW_B, ip + cc, ld ? 16 : 0);
-        }
-        if (last && gl == 0) cp_async4(st + bcell, a.ib.w + (unsigned)ia.x, 4);
-    };
-    auto consume = [&](int buf, int t, int nt, int lo, int stage) {
-        if (t >= nt) return;
-        const int4* rec = rec_of(buf);
-        const unsigned char* st = ring + stage * G::STAGE_B;
-        const int q = lo + t, hi = lo + nt;
-        const int4 ia = rec[2 * t];
-        const float coef = __int_as_float(rec[2 * t + 1].x);
-        const int slot = ia.y, sb = ia.z, se = ia.w;
-        if (q == sb || t == 0) {
+        for (int k = 0; k < KB; ++k) {
+            if (k < cnt) {  // warp-uniform
+                const int q = q0 + k;
+                const int4 ia = ta[k];
+                const float2 pr = tp[k];
+                const float coef = pr.x;
+                const int hu_ = __float_as_int(pr.y) >> kSlotBits;
+                const unsigned char* st = blk + k * G::STAGE_B;
+                const unsigned char* urow = (hu_ ? cache + (hu_ - 1) * G::ROW_B : st) + cell;
+                if (q == ia.z || q == g.lo) {
 #pragma unroll
-            for (int v = 0; v < VPL; ++v) acc[v] = f4_zero();
-            gbias = 0.f;
-            n_row = 0;
-        }
+                    for (int v = 0; v < VPL; ++v) acc[v] = f4_zero();
+                    gbias = 0.f;
+                    n_row = 0;
+                }
 #pragma unroll
-        for (int v = 0; v < VPL; ++v) acc[v] = f4_fma(coef, *(const float4*)(st + v * 512 + cell), acc[v]);
-        gbias += coef;
-        n_row += 1;
-        if (q + 1 == se || q + 1 == hi) {
-            float4 w[VPL];
+                for (int v = 0; v < VPL; ++v) acc[v] = f4_fma(coef, lds4(urow + v * 512), acc[v]);
+                gbias += coef;
+                n_row += 1;
+                if (q + 1 == ia.w || q + 1 == g.hi) {
+                    float4 w[VPL];
+                    float ww = 0.f;
 #pragma unroll
-            for (int v = 0; v < VPL; ++v) w[v] = *(const float4*)(st + G::ROW_B + v * 512 + cell);
-            const float bi = *(const float*)(st + bcell);
-            if (a.reg_w != 0.f) {
-                const float nl = (float)n_row * rw;
+                    for (int v = 0; v < VPL; ++v) {
+                        w[v] = lds4(st + G::ROW_B + v * 512 + cell);
+                        ww += f4_dot(w[v], w[v]);
+                    }
+                    const float bi = *(const float*)(st + bcell);
+                    reg_acc += (float)n_row * (ww + (lane == 0 ? bi * bi : 0.f));  // mf.py:49-54, item side
+                    if (a.reg_w != 0.f) {
+                        const float nl = (float)n_row * rw;
 #pragma unroll
-                for (int v = 0; v < VPL; ++v) acc[v] = f4_fma(nl, w[v], acc[v]);
-                gbias += nl * bi;
+                        for (int v = 0; v < VPL; ++v) acc[v] = f4_fma(nl, w[v], acc[v]);
+                        gbias += nl * bi;
+                    }
+                    flush_row<VPL, FULL, KIND>(a.ie, a.ib, a.pv.i_ticket, a.i_slot_map, nullptr, lane, D, skip, a.release, os,
+                                               ia.y, ia.x, row_parts(ia.z, ia.w), w, acc, bi, gbias);
+                }
             }
-            flush_row<LPR, VPL, FULL, KIND>(a.ie, a.ib, a.pv.i_ticket, a.i_slot_map, nullptr, gmask, gl, lane_base, D, skip,
-                                            a.release, os, slot, ia.x, row_parts(sb, se, lo, hi), w, acc, bi, gbias);
         }
     };
-    walk_stream<LPR, S, TR>(n, a.unit_shift, a.pv.i_cuts, a.pv.hdr + 3, lane, load_rec, issue, consume);
 
+    UnitGen gi, gc;
+    gi.seq = gc.seq = -1;
+    gi.slot = gc.slot = NT - 1;
+    gi.base = gc.base = gi.lo = gc.lo = gi.hi = gc.hi = gi.p = gc.p = 0;
+    gi.valid = gc.valid = true;
+    for (int s = 0; s < PD; ++s) issue_tile(s);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncwarp();
+    for (int b = 0; b < NB - 1; ++b) {
+        issue_block(gi, b);
+        cp_async_commit();
+    }
+    int cslot = 0, islot = NB - 1;
+    for (;;) {
+        cp_async_wait<NB - 2>();
+        __syncwarp();
+        issue_block(gi, islot);
+        cp_async_commit();
+        if (gc.valid && gc.p >= gc.hi) enter(gc, false);
+        if (!gc.valid) break;
+        const int q0 = gc.p, cnt = min(KB, gc.hi - gc.p);
+        gc.p += cnt;
+        consume(gc, q0, cnt, cslot);
+        cslot = cslot + 1 == NB ? 0 : cslot + 1;
+        islot = islot + 1 == NB ? 0 : islot + 1;
+    }
+    cp_async_wait<0>();
+
+    reg_acc = warp_sum(reg_acc);
+    if (lane == 0) s_red[warp] = reg_acc;
+    __syncthreads();
+    if (threadIdx.x == 0 && !skip) {
+        float r = 0.f;
+#pragma unroll
+        for (int q = 0; q < NW; ++q) r += s_red[q];
+        if (r != 0.f) atomicAdd(&a.ws->reg_sum, (double)r);
+    }
     if (!a.finalize) return;
     // last block: global-bias step (its gradient was summed by the users kernel), publish, reset
     __threadfence();
@@ -900,9 +1078,8 @@ __global__ void __launch_bounds__(NW * 32) mf_item_rows_kernel(const RowArgs a) 
     *a.i_count = 0;
 }
 
-// The ring lives in shared memory, which is carved out of the same 228 KB as the L1 cache: the blocks per
-// SM are capped so that the rings take about half of it and the Zipf-hot item rows still hit L1 (with all
-// of it given to rings the L1 hit rate fell to 5% and every hot-row read went to the same two L2 slices).
+// The rings and the hot-row cache live in shared memory, which is carved out of the same 228 KB as L1; the
+// hot rows no longer depend on L1, so the CTAs may take most of the array.
 int g_rows_blocks_per_sm = 0;  // 0 = default below; diagnostics: brs_debug_set_mf_rows_shape
 template <class K>
 int launch_persistent(K kernel, int threads, int smem_bytes, const RowArgs& a, cudaStream_t st) {
@@ -911,7 +1088,7 @@ int launch_persistent(K kernel, int threads, int smem_bytes, const RowArgs& a, c
     int per_sm = 1;
     BRS_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, (size_t)smem_bytes));
     if (per_sm < 1) per_sm = 1;
-    int want = g_rows_blocks_per_sm > 0 ? g_rows_blocks_per_sm : (120 * 1024) / (smem_bytes + 1024);
+    int want = g_rows_blocks_per_sm > 0 ? g_rows_blocks_per_sm : (210 * 1024) / (smem_bytes + 1024);
     if (want < 1) want = 1;
     if (per_sm > want) per_sm = want;
     // ask for the smallest carve-out that holds per_sm blocks; the rest of the 228 KB is L1
@@ -944,60 +1121,37 @@ int check_model(const brs_mf_model* m, int which) {
     return BRS_OK;
 }
 
-int g_rows_stages = 2, g_rows_warps = 2;  // diagnostics: brs_debug_set_mf_rows_shape
-int g_unit_shift = 1;                     // nominal work unit = 2 stream positions per lane group
-int g_rows_only = 0;                      // diagnostics: 1 = users kernel only, 2 = items kernel only
-long long* g_rows_prof = nullptr;         // BRS_ROWS_PROFILE builds: device [65536][8] cycle counters
+int g_rows_blocks = 2, g_rows_warps = 8, g_rows_kb = 2;  // ring blocks per warp / warps per CTA / positions per block
+int g_rows_only = 0;                                     // diagnostics: 1 = users kernel only, 2 = items kernel only
 
 template <int LOSS, int KIND>
 int launch_rows(const RowArgs& a, cudaStream_t st) {
     const int D = a.dim;
-    // a row of D floats = LPR lanes x VPL float4 with VPL = 4 wherever D allows (D = 128 -> 8 lanes x 4): every
-    // warp instruction -- record reads, address math, the sigmoid / loss chain, range tests -- serves 32/LPR
-    // stream positions at once
-#define BRS_ROWS_SN(LPR, VPL, FULL, S, NW)                                                                     \
-    do {                                                                                                       \
-        int rc_ = BRS_OK;                                                                                      \
-        if (g_rows_only != 2)                                                                                  \
-            rc_ = launch_persistent(mf_user_rows_kernel<LPR, VPL, FULL, LOSS, KIND, S, NW>, NW * 32,           \
-                                    NW * RingGeom<LPR, VPL, S, 3>::WARP_B, a, st);                             \
-        if (rc_ != BRS_OK) return rc_;                                                                         \
-        if (g_rows_only != 1)                                                                                  \
-            rc_ = launch_persistent(mf_item_rows_kernel<LPR, VPL, FULL, KIND, S, NW>, NW * 32,                 \
-                                    NW * RingGeom<LPR, VPL, S, 2>::WARP_B, a, st);                             \
-        if (rc_ != BRS_OK) return rc_;                                                                         \
+#define BRS_ROWS_SN(VPL, FULL, NB, NW, KB)                                                                  \
+    do {                                                                                                    \
+        int rc_ = BRS_OK;                                                                                   \
+        if (g_rows_only != 2)                                                                               \
+            rc_ = launch_persistent(mf_user_rows_kernel<VPL, FULL, LOSS, KIND, NB, NW, KB>, NW * 32,        \
+                                    NW * RingGeom<VPL, NB, KB, 3, 32>::WARP_B + RingGeom<VPL, NB, KB, 3, 32>::CACHE_B, a, st); \
+        if (rc_ != BRS_OK) return rc_;                                                                      \
+        if (g_rows_only != 1)                                                                               \
+            rc_ = launch_persistent(mf_item_rows_kernel<VPL, FULL, KIND, NB, NW, KB>, NW * 32,              \
+                                    NW * RingGeom<VPL, NB, KB, 2, 24>::WARP_B + RingGeom<VPL, NB, KB, 2, 24>::CACHE_B, a, st); \
+        if (rc_ != BRS_OK) return rc_;                                                                      \
     } while (0)
-#define BRS_ROWS(LPR, VPL, FULL) BRS_ROWS_SN(LPR, VPL, FULL, 2, 2)
-    if (D == 128 && (g_rows_stages != 2 || g_rows_warps != 2)) {  // tuning sweep of the benchmark shape
-        if (g_rows_stages == 3 && g_rows_warps == 2) BRS_ROWS_SN(8, 4, true, 3, 2);
-        else if (g_rows_stages == 2 && g_rows_warps == 4) BRS_ROWS_SN(8, 4, true, 2, 4);
-        else if (g_rows_stages == 3 && g_rows_warps == 4) BRS_ROWS_SN(8, 4, true, 3, 4);
-        else if (g_rows_stages == 4 && g_rows_warps == 2) BRS_ROWS_SN(8, 4, true, 4, 2);
+    // a row of D floats = 32 lanes x VPL float4 (lanes past dim idle for dim < 128)
+    if (D == 128 && (g_rows_blocks != 2 || g_rows_warps != 8 || g_rows_kb != 2)) {  // tuning sweep of the benchmark shape
+        if (g_rows_blocks == 2 && g_rows_warps == 4 && g_rows_kb == 2) BRS_ROWS_SN(1, true, 2, 4, 2);
+        else if (g_rows_blocks == 2 && g_rows_warps == 16 && g_rows_kb == 2) BRS_ROWS_SN(1, true, 2, 16, 2);
+        else if (g_rows_blocks == 2 && g_rows_warps == 8 && g_rows_kb == 4) BRS_ROWS_SN(1, true, 2, 8, 4);
+        else if (g_rows_blocks == 3 && g_rows_warps == 8 && g_rows_kb == 2) BRS_ROWS_SN(1, true, 3, 8, 2);
         else return BRS_ERR_INVALID_ARG;
-        BRS_CUDA_CHECK(cudaGetLastError());
-        return BRS_OK;
-    }
-    switch (D) {
-        case 4: BRS_ROWS(1, 1, true); break;
-        case 8: BRS_ROWS(1, 2, true); break;
-        case 16: BRS_ROWS(1, 4, true); break;
-        case 32: BRS_ROWS(2, 4, true); break;
-        case 64: BRS_ROWS(4, 4, true); break;
-        case 128: BRS_ROWS(8, 4, true); break;
-        case 256: BRS_ROWS(16, 4, true); break;
-        case 384: BRS_ROWS(32, 3, true); break;
-        case 512: BRS_ROWS(32, 4, true); break;
-        default:  // any other multiple of 4: next power-of-two lane group, tail lanes idle
-            if (D < 8) BRS_ROWS(2, 1, false);
-            else if (D < 16) BRS_ROWS(4, 1, false);
-            else if (D < 32) BRS_ROWS(8, 1, false);
-            else if (D < 64) BRS_ROWS(16, 1, false);
-            else if (D < 128) BRS_ROWS(32, 1, false);
-            else if (D < 256) BRS_ROWS(32, 2, false);
-            else if (D < 384) BRS_ROWS(32, 3, false);
-            else BRS_ROWS(32, 4, false);
-    }
-#undef BRS_ROWS
+    } else if (D == 128) BRS_ROWS_SN(1, true, 2, 8, 2);
+    else if (D < 128) BRS_ROWS_SN(1, false, 2, 8, 2);
+    else if (D == 256) BRS_ROWS_SN(2, true, 2, 4, 2);
+    else if (D < 256) BRS_ROWS_SN(2, false, 2, 4, 2);
+    else if (D <= 384) BRS_ROWS_SN(3, false, 2, 2, 2);
+    else BRS_ROWS_SN(4, false, 2, 2, 2);
 #undef BRS_ROWS_SN
     BRS_CUDA_CHECK(cudaGetLastError());
     return BRS_OK;
@@ -1012,34 +1166,17 @@ extern "C" int64_t brs_mf_plan_bytes(int64_t batch_capacity, int32_t user_capaci
     return (int64_t)plan_view(nullptr, batch_capacity, user_capacity, item_capacity).bytes;
 }
 
-extern "C" int brs_debug_mf_rows_profile(long long* host_out, int n_warps) {
-#ifdef BRS_ROWS_PROFILE
-    if (!g_rows_prof) {
-        BRS_CUDA_CHECK(cudaMalloc(&g_rows_prof, 65536 * 8 * sizeof(long long)));
-        BRS_CUDA_CHECK(cudaMemset(g_rows_prof, 0, 65536 * 8 * sizeof(long long)));
-    }
-    if (host_out && n_warps > 0)
-        BRS_CUDA_CHECK(cudaMemcpy(host_out, g_rows_prof, (size_t)(n_warps < 65536 ? n_warps : 65536) * 8 * sizeof(long long),
-                                  cudaMemcpyDeviceToHost));
-    return BRS_OK;
-#else
-    (void)host_out;
-    (void)n_warps;
-    return BRS_ERR_UNSUPPORTED;
-#endif
-}
-
 extern "C" int brs_debug_set_mf_rows_only(int which) {
     g_rows_only = which;
     return BRS_OK;
 }
 
-extern "C" int brs_debug_set_mf_rows_shape(int stages, int warps_per_block, int blocks_per_sm, int unit_shift) {
-    if (unit_shift < 0 || unit_shift > 3) return BRS_ERR_INVALID_ARG;  // unit <= 8: tiles hold 16 records
-    g_rows_stages = stages;
+extern "C" int brs_debug_set_mf_rows_shape(int ring_blocks, int warps_per_block, int blocks_per_sm, int block_positions) {
+    if (ring_blocks < 2 || ring_blocks > 3 || (block_positions != 2 && block_positions != 4)) return BRS_ERR_INVALID_ARG;
+    g_rows_kb = block_positions;
+    g_rows_blocks = ring_blocks;
     g_rows_warps = warps_per_block;
     g_rows_blocks_per_sm = blocks_per_sm;
-    g_unit_shift = unit_shift;
     return BRS_OK;
 }
 
@@ -1060,7 +1197,8 @@ extern "C" int brs_mf_plan_build(const brs_mf_model* model, int32_t which, int32
     a.third = third;
     a.batch = batch;
     a.n_cols = loss_kind == LOSS_BPR ? 2 : 1;
-    a.unit_shift = g_unit_shift;
+    // the hot index travels in the spare high bits of slots / stream positions
+    a.hot_reads = (pl.user_capacity < (1 << kSlotBits) && 2 * batch < (1ll << kPosBits) - 1) ? kHotReads : 0x7fffffff;
     a.err = &((brs_step_ws*)model->ws)->err_pending[which];
     cudaStream_t st = (cudaStream_t)stream;
     if (batch > 0) {
@@ -1081,13 +1219,6 @@ extern "C" int brs_mf_plan_build(const brs_mf_model* model, int32_t which, int32
         const long long cap = (long long)brs_sm_count() * 4;
         if (blocks > cap) blocks = cap;
         mf_plan_fill_kernel<<<(int)blocks, kPlanThreads, 0, st>>>(a);
-    }
-    {
-        const long long units = ((2 * batch) >> a.unit_shift) + 2;
-        long long blocks = (units + kPlanThreads - 1) / kPlanThreads;
-        const long long cap = (long long)brs_sm_count() * 2;
-        if (blocks > cap) blocks = cap;
-        mf_plan_cuts_kernel<<<dim3((unsigned)blocks, 2u), kPlanThreads, 0, st>>>(a);
     }
     BRS_CUDA_CHECK(cudaGetLastError());
     return BRS_OK;
@@ -1116,7 +1247,6 @@ extern "C" int brs_mf_step_planned(const brs_mf_model* model, int32_t which, con
     const bool dense = opt->kind != BRS_SGD && opt->mode == BRS_DENSE;
     RowArgs a;
     memset(&a, 0, sizeof(a));
-    a.prof = g_rows_prof;
     a.ue = row_table(model->user.table[0]);
     a.ub = row_table(model->user.table[1]);
     a.ie = row_table(model->item.table[0]);
@@ -1137,7 +1267,6 @@ extern "C" int brs_mf_step_planned(const brs_mf_model* model, int32_t which, con
     a.opt.eps = opt->eps;
     a.opt.alpha = opt->alpha;
     a.dim = D;
-    a.unit_shift = g_unit_shift;
     a.reg_w = reg_weight;
     a.inv_b = batch > 0 ? 1.0f / (float)batch : 0.f;
     a.release = dense ? 0 : 1;

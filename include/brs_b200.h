@@ -251,16 +251,13 @@ int brs_mf_step(const brs_mf_model *model, const brs_opt *opt, int32_t loss_kind
                 const int64_t *items, const void *third, int64_t batch, float reg_weight,
                 float *out /* brs_step_out */, void *stream);
 
-/* diagnostics: ring stages (2..4) and warps per block (2 | 4) of the two row kernels (dim 128 only), the
- * cap on resident blocks per SM (0 = default: rings take about half of the L1 / shared-memory array), and
- * log2 of the nominal work-unit length (0..3; plans built afterwards use it) */
-int brs_debug_set_mf_rows_shape(int stages, int warps_per_block, int blocks_per_sm, int unit_shift);
+/* diagnostics: ring blocks per warp (2 | 3), warps per CTA (2 | 4 | 8) of the two row kernels (dim 128
+ * only), the cap on resident CTAs per SM (0 = default: the rings leave L1 a share of the array) and the
+ * stream positions per block (2 | 4) */
+int brs_debug_set_mf_rows_shape(int ring_blocks, int warps_per_block, int blocks_per_sm, int block_positions);
 /* diagnostics (per-kernel timing on a FIXED plan; leaves the step incomplete): 0 = both row kernels,
  * 1 = users kernel only, 2 = items kernel only */
 int brs_debug_set_mf_rows_only(int which);
-/* diagnostics, only in builds with -DBRS_ROWS_PROFILE (else BRS_ERR_UNSUPPORTED): per-warp clock64 phase
- * counters of the users kernel, 8 int64 per warp; the first call (host_out NULL) allocates the buffer */
-int brs_debug_mf_rows_profile(long long *host_out, int n_warps);
 
 /* MF.predict / MF.forward under no_grad (beta_rec/models/mf.py:57-70): scores[k] = sigmoid(...) */
 int brs_mf_predict(const brs_mf_model *model, const int64_t *users, const int64_t *items, int64_t n,

@@ -17,6 +17,45 @@ from tests.test_oracle_golden import BUDGET, check_adaptive_step, check_params_a
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True, params=["scratch", "rows"])
+def step_impl(request, monkeypatch):
+    """Every MF test runs against both implementations of the training step (gradient-scratch kernels
+    and the row-owner kernels): the engine default is switched, nothing else."""
+    from beta_recsys_b200.engines import mf
+
+    monkeypatch.setattr(mf, "DEFAULT_STEP_IMPL", request.param)
+    return request.param
+
+
+def check_update(before, got, want, what="", tol=1e-4, row_tol=1e-3, cond=None, lr=0.0):
+    """The UPDATE of one step, not the parameters: (got - before) against (want - before).
+
+    Relative to the parameter's scale (max|w| ~ 0.4) a wrong gradient on a once-touched row (|dw| ~ 1e-8 at
+    config 2) is invisible, so the error is measured against the update itself:
+      * per tensor: |d_got - d_want| <= tol * max|d_want|                       (tol 1e-4)
+      * per row   : |d_got - d_want| <= row_tol * max|d_want[row]|              (row_tol 1e-3: catches one wrong row)
+    each plus 2 ulp of the fp32 parameter (both sides round w - lr*g to fp32; at config 2 one ulp of w is
+    already 3e-4 of max|dw|, which no fp32 implementation can beat).  Bias gradients add opposite-sign
+    terms (c_pos < 0 < c_neg) that cancel almost completely -- the global bias sums 2B of them -- so with
+    cond = O.mf_condition_scale(...) the fp32 summation's own forward error 4e-6 * lr * sum|terms| is allowed too.
+    """
+    for k in want:
+        b64 = before[k].astype(np.float64)
+        dg, dw = got[k].astype(np.float64) - b64, want[k].astype(np.float64) - b64
+        ulp = 2.0 * np.spacing(np.maximum(np.abs(want[k]), np.abs(before[k])).astype(np.float32)).astype(np.float64)
+        if cond is not None and before[k].shape[-1] == 1:
+            ulp = ulp + 4e-6 * lr * float(cond[k])
+        err = np.abs(dg - dw)
+        top = float(np.abs(dw).max())
+        assert top > 0 or k == "global_bias", (what, k, "the oracle did not move this tensor")
+        bad = err > tol * top + ulp
+        assert not bad.any(), (what, k, "tensor-relative", float((err - ulp).max() / max(top, 1e-30)))
+        if dw.ndim == 2:
+            row_top = np.abs(dw).max(axis=1, keepdims=True)
+            bad = err > row_tol * row_top + ulp
+            assert not bad.any(), (what, k, "row-relative", int(np.argwhere(bad)[0][0]))
+
+
 def make_engine(n_users, n_items, d, batch, optimizer, lr, loss="bpr", adam_mode="dense", reg=None, state=None):
     from beta_recsys_b200.engines import MFEngine
 
@@ -131,8 +170,12 @@ def test_mf_matches_reference_golden(name):
                 assert abs(loss - ol) <= 1e-5 * max(1, abs(ol)) and abs(reg - orr) <= 1e-5 * max(1, abs(orr))
                 check_adaptive_step(before, snap(eng), opt_snap(eng), ref_opt, m["optimizer"], m["lr"], t + 1)
                 check_params_adaptive(snap(eng), op, before, m["lr"], 1)
-        elif t == 0:
-            sc.check(snap(eng), g.group("after1"), what="after1")
+        else:
+            if t == 0:
+                sc.check(snap(eng), g.group("after1"), what="after1")
+                check_update(before, snap(eng), g.group("after1"), what="after1 (reference)")
+            _, _, op, _ = oracle_step_from_gpu_state(before, opt_before, t, (b["users"][t], b["pos"][t], last), m)
+            check_update(before, snap(eng), op, what="step %d" % t)
     if adaptive:  # hard bound only: |dp| <= 2*lr per step whatever the rounding
         for k, v in g.group("after5").items():
             assert np.abs(snap(eng)[k] - v).max() <= 2.02 * m["lr"] * 5, k
@@ -156,9 +199,14 @@ def test_mf_sgd_all_dims_vs_oracle(d, loss):
         u, i = zipf_ids(rng, nu, bsz), zipf_ids(rng, ni, bsz)
         third = rng.integers(0, ni, bsz) if loss == "bpr" else (rng.random(bsz) < 0.3).astype(np.float32)
         sc.add_step(p, (u, i, third), loss, 0.05)
+        before = snap(eng)
         l, r = eng.train_single_batch(cuda_batch(u, i, third))
         ol, orr = O.mf_train_single_batch(p, st, (u, i, third), loss, "sgd", 0.05, 0.0)
         assert abs(l - ol) <= 1e-5 * max(1, abs(ol)) and abs(r - orr) <= 1e-5 * max(1, abs(orr)), (t, l, ol, r, orr)
+        # this step's update against one oracle step from the GPU's own pre-step state
+        q = {k: v.copy() for k, v in before.items()}
+        O.mf_train_single_batch(q, O.new_opt_state(q, "sgd"), (u, i, third), loss, "sgd", 0.05, 0.0)
+        check_update(before, snap(eng), q, what="step %d" % t)
     sc.check(snap(eng), p)
 
 
@@ -480,7 +528,9 @@ def test_mf_full_size_config2_vs_oracle_and_properties():
     assert abs(l - loss) <= 1e-5 * max(1, loss) and abs(r - reg) <= 1e-5 * max(1, reg)
     sc = Scale(before)
     sc.add_step(before, (u, i, j), "bpr", lr)
-    sc.check(after, {k: before[k] - np.float32(lr) * g[k] for k in before})
+    want = {k: before[k] - np.float32(lr) * g[k] for k in before}
+    sc.check(after, want)
+    check_update(before, after, want, what="config 2", cond=O.mf_condition_scale(before, (u, i, j), "bpr"), lr=lr)
     # properties: rows outside the batch are bit-identical; scratch is clean again
     mask = np.ones(nu, dtype=bool)
     mask[u] = False
