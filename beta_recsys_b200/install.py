@@ -19,6 +19,9 @@ _BINDINGS = [
     ("beta_rec.models.mlp", "MLPEngine", "MLPEngine"),
     ("beta_rec.recommenders.lightgcn", "LightGCNEngine", "LightGCNEngine"),
     ("beta_rec.models.lightgcn", "LightGCNEngine", "LightGCNEngine"),
+    # ranking evaluation: train_eval_worker / test_eval_worker look `evaluate` up at call time
+    # (beta_rec/core/eval_engine.py:106,109)
+    ("beta_rec.core.eval_engine", "evaluate", "eval.evaluate"),
 ]
 _saved = {}
 
@@ -42,7 +45,12 @@ def install(strict=False):
                 raise AttributeError("%s has no attribute %s" % (mod_name, attr))
             continue
         _saved.setdefault((mod_name, attr), getattr(mod, attr))
-        setattr(mod, attr, getattr(engines, ours))
+        if ours.startswith("eval."):
+            from . import eval as _eval
+
+            setattr(mod, attr, getattr(_eval, ours[5:]))
+        else:
+            setattr(mod, attr, getattr(engines, ours))
         done.append((mod_name, attr))
     return done
 

@@ -501,6 +501,22 @@ int brs_scatter_add(float *table, int64_t n_rows, int32_t dim, const int64_t *id
 int brs_gather_sgd_update(float *table, int64_t n_rows, int32_t dim, const int64_t *idx, int64_t n, float lr,
                           float *out, void *stream);
 
+/* ---- ranking evaluation: beta_rec/core/eval_engine.py:49-87 (evaluate), beta_rec/utils/evaluation.py:459-785 ----
+ * ndcg / map / precision / recall at k of `n_pred` prediction rows (user, item, score) against `n_true`
+ * true rows (user, item, rating; only rating >= 1 counts, evaluation.py:492), as the reference's pandas code
+ * defines them: per user the k highest scores (equal scores keep the frame's row order: nlargest
+ * keep="first" + rank(method="first")), hits = top-k rows whose (user, item) is a true row, users = users with
+ * at least one true row and one prediction row.  User ids lie in [0, n_user_ids), item ids in [0, 2^32).
+ * out[8] (double, device): {sum_u ndcg_u, sum_u ap_u, sum_u hit_u / k, sum_u hit_u / actual_u, users, hits,
+ * status (1 = an id was out of range), 0}; the caller divides the sums by `users` (0.0 when hits == 0,
+ * evaluation.py:627).  workspace: brs_rank_metrics_workspace_bytes(...) bytes of device memory, any content.
+ * 1 <= k <= 1024.  Stream-ordered, no host synchronisation. */
+int64_t brs_rank_metrics_workspace_bytes(int64_t n_true, int64_t n_pred, int64_t n_user_ids);
+int brs_rank_metrics(const int64_t *true_users, const int64_t *true_items, const float *true_ratings, int64_t n_true,
+                     const int64_t *pred_users, const int64_t *pred_items, const float *pred_scores, int64_t n_pred,
+                     int64_t n_user_ids, int32_t k, void *workspace, int64_t workspace_bytes, double *out,
+                     void *stream);
+
 #ifdef __cplusplus
 }
 #endif
