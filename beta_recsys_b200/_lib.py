@@ -176,6 +176,10 @@ _PROTOTYPES = {
     "brs_gather": (C.c_int, [_P, C.c_int64, C.c_int32, _P, C.c_int64, _P, _P]),
     "brs_scatter_add": (C.c_int, [_P, C.c_int64, C.c_int32, _P, C.c_int64, _P, C.c_float, _P]),
     "brs_gather_sgd_update": (C.c_int, [_P, C.c_int64, C.c_int32, _P, C.c_int64, C.c_float, _P, _P]),
+    "brs_pairset_bytes": (C.c_int64, [C.c_int64]),
+    "brs_pairset_build": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int64, _P, C.c_int64, _P]),
+    "brs_sample_negatives": (C.c_int, [_P, C.c_int64, _P, C.c_int64, C.c_int64, C.c_int32, C.c_uint64, _P, _P]),
+    "brs_pairset_status": (C.c_int, [_P, C.POINTER(C.c_uint32), _P]),
     "brs_rank_metrics_workspace_bytes": (C.c_int64, [C.c_int64, C.c_int64, C.c_int64]),
     "brs_rank_metrics": (C.c_int, [_P, _P, _P, C.c_int64, _P, _P, _P, C.c_int64, C.c_int64, C.c_int32, _P, C.c_int64, _P, _P]),
 }

@@ -517,6 +517,22 @@ int brs_rank_metrics(const int64_t *true_users, const int64_t *true_items, const
                      int64_t n_user_ids, int32_t k, void *workspace, int64_t workspace_bytes, double *out,
                      void *stream);
 
+/* ---- negative sampling: BaseData.instance_bpr_loader / instance_bce_loader (beta_rec/data/base_data.py:182-253) ----
+ * brs_pairset_build puts the training interactions (user, item) into a device hash set (`set`:
+ * brs_pairset_bytes(n) bytes).  brs_sample_negatives then writes, for every row r of `users`, `num_negative`
+ * pairwise distinct items drawn uniformly from the items users[r] has NOT interacted with (the reference's
+ * `random.sample(set(item_id_pool) - positive_items, num_negative)`), by rejection on the counter-based stream
+ *     candidate(r, t, attempt) = mix64(seed + r*C1 + t*C2 + attempt*C3) mod n_items
+ * (splitmix64 finaliser; constants in csrc/sample_kernels.cu), a pure function of its arguments.
+ * neg_out: int64 [n, num_negative], 1 <= num_negative <= 64.  brs_pairset_status (synchronises) reports
+ * bit 0 = an interaction outside [0, n_users) x [0, n_items), bit 1 = a user had no item left. */
+int64_t brs_pairset_bytes(int64_t n_pairs);
+int brs_pairset_build(const int64_t *users, const int64_t *items, int64_t n, int64_t n_users, int64_t n_items, void *set,
+                      int64_t set_bytes, void *stream);
+int brs_sample_negatives(const void *set, int64_t n_pairs_in_set, const int64_t *users, int64_t n, int64_t n_items,
+                         int32_t num_negative, uint64_t seed, int64_t *neg_out, void *stream);
+int brs_pairset_status(const void *set, uint32_t *status_out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
