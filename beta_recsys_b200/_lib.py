@@ -133,7 +133,6 @@ _PROTOTYPES = {
     "brs_mf_step_planned": (C.c_int, [C.POINTER(MfModel), C.c_int32, C.POINTER(Opt), C.c_int32, C.c_int64, C.c_float,
                                       _P, _P]),
     "brs_debug_set_mf_rows_only": (C.c_int, [C.c_int]),
-    "brs_debug_set_mf_rows_shape": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "brs_mf_step": (C.c_int, [C.POINTER(MfModel), C.POINTER(Opt), C.c_int32, _P, _P, _P, C.c_int64, C.c_float, _P,
                               _P]),
     "brs_ncf_fwd_bwd": (C.c_int, [C.POINTER(NcfModel), _P, _P, _P, C.c_int64, _P]),
@@ -176,6 +175,9 @@ _PROTOTYPES = {
     "brs_gather": (C.c_int, [_P, C.c_int64, C.c_int32, _P, C.c_int64, _P, _P]),
     "brs_scatter_add": (C.c_int, [_P, C.c_int64, C.c_int32, _P, C.c_int64, _P, C.c_float, _P]),
     "brs_gather_sgd_update": (C.c_int, [_P, C.c_int64, C.c_int32, _P, C.c_int64, C.c_float, _P, _P]),
+    "brs_adj_workspace_bytes": (C.c_int64, [C.c_int64, C.c_int64, C.c_int64]),
+    "brs_adj_build": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int64, C.c_int32, _P, C.c_int64, _P, _P, _P, _P, _P, _P, _P]),
+    "brs_adj_status": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int64, C.POINTER(C.c_uint32), _P]),
     "brs_pairset_bytes": (C.c_int64, [C.c_int64]),
     "brs_pairset_build": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int64, _P, C.c_int64, _P]),
     "brs_sample_negatives": (C.c_int, [_P, C.c_int64, _P, C.c_int64, C.c_int64, C.c_int32, C.c_uint64, _P, _P]),

@@ -11,15 +11,15 @@
 //                     (block sum + one atomicAdd on the stream cursor; the order of segments is free)
 //            fill     one thread per sample: its record in the USER stream (samples grouped by user row)
 //                     and its one or two entries in the ITEM stream (entries grouped by item row)
-//   users  one warp per work unit of the user stream (about 16 samples; a unit never cuts a short row):
-//          per block of 4 samples the rows are gathered by cp.async (one warp instruction per 512-byte
-//          row at dim 128; the next block is in flight while this one is processed), the block's 8 dots
-//          are reduced by ONE transposing butterfly so that the sigmoid / loss chain runs once per block,
-//          the user-row gradient is accumulated in registers while the user stays the same; at the end
-//          of a row: PRE-step row -> staging table, updated row -> table, in place; per sample
-//          (coefficient, user slot) -> the item stream
-//   items  same walk over the item stream: sum of coefficient * staged user row in registers, updated
-//          item row in place; last block: global-bias step + brs_step_out
+//   users  one warp per work unit of the user stream (about 16 samples; a unit never cuts a short row),
+//          rows in registers: per block of 4 samples the rows are gathered with 128-bit read-only loads
+//          (one warp instruction per 512-byte row at dim 128, the whole block in flight at once), the
+//          block's 8 dots are reduced by ONE transposing butterfly so that the sigmoid / loss chain runs
+//          once per block, the user-row gradient is accumulated in registers while the user stays the
+//          same; at the end of a row: PRE-step row -> staging table, updated row -> table, in place; per
+//          sample (coefficient, user slot) -> the item stream
+//   items  same decomposition of the item stream -- a row-per-warp SpMM: sum of coefficient * staged user
+//          row in registers, updated item row in place; last block: global-bias step + brs_step_out
 //
 // Batch-synchronous semantics hold because item rows are only written by `items` (after every gather
 // of `users` has completed: kernel boundary), `items` reads user rows only from the staging copy, and a
@@ -44,23 +44,12 @@ constexpr int kPlanThreads = 256;
 constexpr int kPlanWarps = kPlanThreads / 32;
 #define BRS_SLOT_OVERFLOW (-3)
 
-// Hot rows.  A 512-byte row lives in two L2 slices and a slice serves about one 32-byte sector per clock, so
-// a row that is gathered thousands of times in one step (Zipf head: the hottest item is ~10% of a batch, the
-// hottest user likewise) serialises the whole kernel on those two slices (round-2 profile: both row kernels
-// sat at ~35 us with every pipe idle, whatever their instruction count or occupancy).  The plan therefore
-// lists the rows gathered at least kHotReads times and every CTA of the row kernels keeps them in shared
-// memory; records carry (hot index + 1) in spare high bits, 0 = gather from global memory as usual.
-constexpr int kHotRows = 32;
-constexpr int kHotReads = 384;
-constexpr int kSlotBits = 20;  // s_a.y / ipair.y = user slot | (hot + 1) << kSlotBits
-constexpr int kPosBits = 24;   // s_b.x / s_b.y   = item-stream position | (hot + 1) << kPosBits
 
 // ---------------------------------------------------------------------------
 // plan buffer carve-up (host and device agree through this one function)
 // ---------------------------------------------------------------------------
 struct PlanView {
     int* hdr;        // [64]: 0 = samples in the user stream, 1 = entries in the item stream (segment cursors),
-                     //       4 / 5 = hot user / item rows found by this plan (may exceed kHotRows: clamp)
     int* u_slot;     // [B]   user slot of sample s (-1: sample dropped)
     int* u_rank;     // [B]   rank of s inside its user segment
     int* i_slot;     // [2B]  c*B + s
@@ -69,10 +58,6 @@ struct PlanView {
     int* i_cnt;      // [Ci]
     int2* u_seg;     // [Cu]  {begin, end} of the slot's segment in the user stream
     int2* i_seg;     // [Ci]
-    int* u_hot;      // [Cu]  index of the slot's row in the hot list, -1 = not hot
-    int* i_hot;      // [Ci]
-    int* u_hotlist;  // [kHotRows] user SLOTS whose staged row the items kernel keeps in shared memory
-    int* i_hotlist;  // [kHotRows] item ROW IDS whose row the users kernel keeps in shared memory
     int* u_ticket;   // [Cu]  parts of a multi-part row that have finished (zero between steps)
     int* i_ticket;   // [Ci]
     int4* s_a;       // [B]   user stream position p -> {user row, user slot, pos item, neg item | rating bits}
@@ -100,10 +85,6 @@ __host__ __device__ inline PlanView plan_view(void* buf, long long B, int Cu, in
     BRS_CARVE(i_cnt, int, Ci)
     BRS_CARVE(u_seg, int2, Cu)
     BRS_CARVE(i_seg, int2, Ci)
-    BRS_CARVE(u_hot, int, Cu)
-    BRS_CARVE(i_hot, int, Ci)
-    BRS_CARVE(u_hotlist, int, kHotRows)
-    BRS_CARVE(i_hotlist, int, kHotRows)
     BRS_CARVE(u_ticket, int, Cu)
     BRS_CARVE(i_ticket, int, Ci)
     BRS_CARVE(s_a, int4, B)
@@ -126,7 +107,6 @@ struct PlanArgs {
     const void* third;  // neg ids (int64) or ratings (float)
     long long batch;
     int n_cols;         // 2 = bpr (pos, neg), 1 = bce
-    int hot_reads;      // a row gathered at least this often per step is hot (INT_MAX: packing impossible, none)
     unsigned int* err;  // ws->err_pending[which]
 };
 
@@ -160,8 +140,6 @@ __global__ void __launch_bounds__(kPlanThreads) mf_plan_claim_kernel(const PlanA
     if (blockIdx.x == 0 && threadIdx.x == 0) {  // segment cursors of this plan (consumed by the next kernel)
         a.pv.hdr[0] = 0;
         a.pv.hdr[1] = 0;
-        a.pv.hdr[4] = 0;
-        a.pv.hdr[5] = 0;
     }
     for (long long it = 0; it < n_iter; ++it) {
         const long long s = it * stride + (long long)blockIdx.x * kPlanThreads + threadIdx.x;
@@ -256,11 +234,6 @@ __global__ void __launch_bounds__(kPlanThreads) mf_plan_segment_kernel(const Pla
     const brs_rowset& rs = ent == 0 ? a.urs : a.irs;
     int* cnt = ent == 0 ? a.pv.u_cnt : a.pv.i_cnt;
     int2* seg = ent == 0 ? a.pv.u_seg : a.pv.i_seg;
-    int* hot = ent == 0 ? a.pv.u_hot : a.pv.i_hot;
-    int* hotlist = ent == 0 ? a.pv.u_hotlist : a.pv.i_hotlist;
-    // a user row is gathered once per (sample, item) entry by the items kernel, an item row once per entry
-    // by the users kernel
-    const int reads_per = ent == 0 ? a.n_cols : 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int n = *rs.count;
     if (n > rs.capacity) n = rs.capacity;
@@ -290,13 +263,6 @@ __global__ void __launch_bounds__(kPlanThreads) mf_plan_segment_kernel(const Pla
             const int begin = s_base + s_w[warp] + incl - c;
             seg[k] = make_int2(begin, begin + c);
             cnt[k] = 0;
-            int h = -1;
-            if (c >= (a.hot_reads + reads_per - 1) / reads_per) {
-                h = atomicAdd(a.pv.hdr + 4 + ent, 1);
-                if (h < kHotRows) hotlist[h] = ent == 0 ? k : rs.list[k];
-                else h = -1;
-            }
-            hot[k] = h;
         }
         __syncthreads();
     }
@@ -322,16 +288,15 @@ __global__ void __launch_bounds__(kPlanThreads) mf_plan_fill_kernel(const PlanAr
         const int2 is = a.pv.i_seg[si];
         const int qi = is.x + a.pv.i_rank[s];
         a.pv.i_a[qi] = make_int4(i, si, is.x, is.y);
-        int qj = -1, pj = -1;
+        int qj = -1;
         if (two) {
             const int sj = a.pv.i_slot[B + s];
             const int2 js = a.pv.i_seg[sj];
             qj = js.x + a.pv.i_rank[B + s];
             a.pv.i_a[qj] = make_int4(second, sj, js.x, js.y);
-            pj = qj | ((a.pv.i_hot[sj] + 1) << kPosBits);
         }
-        a.pv.s_a[p] = make_int4(u, su | ((a.pv.u_hot[su] + 1) << kSlotBits), i, second);
-        a.pv.s_b[p] = make_int4(qi | ((a.pv.i_hot[si] + 1) << kPosBits), pj, us.x, us.y);
+        a.pv.s_a[p] = make_int4(u, su, i, second);
+        a.pv.s_b[p] = make_int4(qi, qj, us.x, us.y);
     }
 }
 
@@ -396,7 +361,6 @@ struct RowArgs {
 __device__ __forceinline__ float4 ld4(const float* p) { return *(const float4*)p; }
 __device__ __forceinline__ void st4(float* p, float4 v) { *(float4*)p = v; }
 __device__ __forceinline__ float4 ld4_cg(const float* p) { return __ldcg((const float4*)p); }
-__device__ __forceinline__ float4 lds4(const unsigned char* p) { return *(const float4*)p; }
 
 // The last sample of a row part was accumulated by this warp (lane l holds columns 4*(v*32 + l) .. +3):
 // rows with several parts combine their partial sums through the scratch and the last part to arrive
@@ -469,17 +433,6 @@ __device__ __forceinline__ void flush_row(const RowTable& te, const RowTable& tb
     if (release && lane == 0) slot_map[row] = BRS_SLOT_NONE;
 }
 
-// Ampere-style asynchronous copies (SASS: LDGSTS) global -> shared, tracked by commit groups: at dim 128 one
-// warp instruction moves one 512-byte row, and nothing is held in registers while it flies.  Every lane
-// later reads back exactly the row / bias bytes it copied itself, so cp.async.wait_group is all the
-// synchronisation the rows need; record tiles (read by every lane) add one __syncwarp per block.
-// src_bytes == 0 zero-fills the destination (columns past dim / records past the stream end).
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-
 // Sum over the 32 lanes of NV per-lane values with NV - 1 + log2(32 / NV) shuffles instead of 5 * NV: each
 // halving step exchanges half of the values a lane still carries.  Afterwards lane l holds the complete sum
 // of value (l >> (5 - log2 NV)) & (NV - 1)  (NV = 8: index (l >> 2) & 7; NV = 4: index l >> 3).
@@ -502,57 +455,30 @@ __device__ __forceinline__ float transpose_reduce(float (&v)[NV], int lane) {
     return r;
 }
 
-// A warp's walk over its units: unit number seq of warp gw is unit gw + seq * W of the stream.
-struct UnitGen {
-    int seq;    // units entered so far - 1
-    int slot;   // record tile of the current unit (seq % NT)
-    int base;   // first position the tile covers
-    int lo, hi; // the unit: [lo, hi)
-    int p;      // next position to hand out
-    bool valid;
-};
 
-// geometry of one warp's shared memory: NT record tiles + a ring of NB blocks of KB stages (one per position)
-template <int VPL, int NB, int KB, int NR, int REC_B>
-struct RingGeom {
-    static constexpr int NT = 2 * NB - 1;  // tiles alive: NB - 1 behind the issue pointer, it, NB - 1 prefetched
-    static constexpr int PD = NB - 1;      // tile prefetch distance in units
-    static constexpr int ROW_B = VPL * 512;
-    static constexpr int BIAS_OFF = NR * ROW_B;
-    static constexpr int STAGE_B = NR * ROW_B + 128;  // + one 4-byte cell per lane
-    static constexpr int TILE_B = kTile * REC_B;
-    static constexpr int WARP_B = NT * TILE_B + NB * KB * STAGE_B;
-    static constexpr int CACHE_B = kHotRows * ROW_B;  // per CTA, after the warps' regions
-};
+constexpr int kRowWarps = 8;  // warps (= work units) per CTA of the row kernels
+constexpr int kRowThreads = kRowWarps * 32;
 
-__device__ __forceinline__ void cp_async16_s(uint32_t dst, const void* gsrc, int src_bytes) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(gsrc), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async16_sf(uint32_t dst, const void* gsrc) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async4_s(uint32_t dst, const void* gsrc) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(gsrc) : "memory");
-}
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg((const float4*)p); }
 
-// users kernel: one warp walks units of the user stream, KB positions per block.
-//   issue    per position: pos / neg item rows (+ the user row at the first position of a row part) and the
-//            three biases (lanes 0..2) by cp.async into the block's ring slot
-//   phase 1  per position: per-lane partial dots u.i, u.j (+ the bias a lane copied)
-//   phase 2  ONE transposing reduction for the block's 2*KB dots, then the sigmoid / loss / d loss chain
-//            once per block (lane group k works on position k); (coefficient, user slot) -> item stream
-//   phase 3  per position: gradient of the user row accumulated in registers; at the end of a row part:
-//            regularizer term of the row, PRE-step row -> staging table, updated row -> table
-template <int VPL, bool FULL, int LOSS, int KIND, int NB, int NW, int KB>
-__global__ void __launch_bounds__(NW * 32) mf_user_rows_kernel(const RowArgs a) {
+// users kernel: ONE WARP PER WORK UNIT of the user stream, everything in registers (the only shared memory
+// is the unit's record tile); rows are gathered with plain 128-bit read-only loads -- one warp instruction
+// per 512-byte row at dim 128, up to 12 in flight per warp, ~20 warps per SM -- so the Zipf-hot rows hit L1
+// and nothing has to be staged.  Per block of 4 samples:
+//   load     pos / neg item rows (+ the user row at the first sample of a row part), the three biases on
+//            lanes 0..2
+//   phase 1  per-lane partial dots u.i, u.j (+ the bias a lane loaded)
+//   phase 2  ONE transposing reduction for the block's 8 dots, then the sigmoid / loss / d loss chain once
+//            per block (lanes 8k .. 8k+7 work on sample k); (coefficient, user slot) -> item stream
+//   phase 3  gradient of the user row accumulated in registers; at the end of a row part: regularizer term
+//            of the row, PRE-step row -> staging table, updated row -> table
+template <int VPL, bool FULL, int LOSS, int KIND>
+__global__ void __launch_bounds__(kRowThreads) mf_user_rows_kernel(const RowArgs a) {
     constexpr int C = (LOSS == LOSS_BPR) ? 2 : 1;
-    using G = RingGeom<VPL, NB, KB, 3, 32>;
-    constexpr int NT = G::NT, PD = G::PD;
-    constexpr int KSH = KB == 4 ? 3 : 4;  // lanes [k << KSH, (k + 1) << KSH) run the loss chain of position k
-    static_assert(KB == 2 || KB == 4, "block = 2 or 4 positions");
-    extern __shared__ __align__(16) unsigned char smem[];
+    constexpr int K = 4, KSH = 3;
+    __shared__ int4 s_tile[kRowWarps][kTile][2];  // [t][0] = s_a, [t][1] = s_b of stream position base + t
     __shared__ OptScalars s_opt;
-    __shared__ float s_red[3][NW];
+    __shared__ float s_red[3][kRowWarps];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int D = a.dim;
@@ -564,250 +490,163 @@ __global__ void __launch_bounds__(NW * 32) mf_user_rows_kernel(const RowArgs a) 
     const int n = __ldg(a.pv.hdr + 0);
     const float rw = 2.0f * a.reg_w * a.inv_b;  // d(reg_w*regularizer)/d row = rw * row per forward call
     const float fwd_calls = (float)C;
-    const int W = gridDim.x * NW;
-    const int gw = warp * gridDim.x + blockIdx.x;  // consecutive units run on different SMs
     float loss_acc = 0.f, reg_acc = 0.f, gb_acc = 0.f;
-
-    unsigned char* wbase = smem + (size_t)warp * G::WARP_B;
-    int4* tiles = (int4*)wbase;  // tile s: records [2t] = s_a, [2t+1] = s_b
-    unsigned char* ring = wbase + NT * G::TILE_B;
-    const uint32_t tiles_s = smem_u32(tiles), ring_s = smem_u32(ring);
-    const int cell = lane * 16;
-    const int bcell = G::BIAS_OFF + lane * 4;
-    // per-lane constants of the gathers: column of vector v, its validity, the lane's bias table
-    const float* ue_l = a.ue.w + lane * 4;
-    const float* ie_l = a.ie.w + lane * 4;
-    const float* btab = lane == 0 ? a.ub.w : a.ib.w;
-    const bool bias_lane = lane <= C;
-    // the batch's hot item rows (PRE-step: this kernel never writes item rows) -> shared memory, once per CTA
-    const unsigned char* cache = smem + NW * G::WARP_B;
-    {
-        const int nh = min(__ldg(a.pv.hdr + 5), kHotRows);
-        for (int h = warp; h < nh; h += NW) {
-            const float* src = ie_l + (size_t)(unsigned)__ldg(a.pv.i_hotlist + h) * (unsigned)D;
-#pragma unroll
-            for (int v = 0; v < VPL; ++v) {
-                const bool ld = FULL || (v * 32 + lane) * 4 < D;
-                *(float4*)(smem + NW * G::WARP_B + h * G::ROW_B + v * 512 + cell) = ld ? ld4(src + v * 128) : f4_zero();
-            }
-        }
-        __syncthreads();
-    }
-
-    auto issue_tile = [&](int seq) {
-        const int pos = ((gw + seq * W) << kUnitShift) + lane;
-        const bool ok = lane < kTile && pos < n;
-        const uint32_t tl = tiles_s + (seq % NT) * G::TILE_B + lane * 32;
-        if (lane < kTile) {
-            cp_async16_s(tl, a.pv.s_a + (ok ? pos : 0), ok ? 16 : 0);
-            cp_async16_s(tl + 16, a.pv.s_b + (ok ? pos : 0), ok ? 16 : 0);
-        }
-    };
-    auto enter = [&](UnitGen& g, bool prefetch) {  // move on to the warp's next non-empty unit
-        for (;;) {
-            g.seq += 1;
-            g.slot = g.slot + 1 == NT ? 0 : g.slot + 1;
-            if (prefetch) issue_tile(g.seq + PD);
-            const int base = (gw + g.seq * W) << kUnitShift;
-            if (base >= n) {
-                g.valid = false;
-                return;
-            }
-            const int4* tl = tiles + g.slot * (kTile * 2);
-            const int4 r0 = tl[1], r1 = tl[2 * kUnit + 1];
-            g.base = base;
-            g.lo = snap_cut(base, r0.z, r0.w);
-            g.hi = base + kUnit >= n ? n : snap_cut(base + kUnit, r1.z, r1.w);
-            g.p = g.lo;
-            if (g.lo < g.hi) return;
-        }
-    };
-    auto issue_block = [&](UnitGen& g, int rslot) {
-        if (g.valid && g.p >= g.hi) enter(g, true);
-        if (!g.valid) return;
-        const int cnt = min(KB, g.hi - g.p);
-        const int4* tl = tiles + g.slot * (kTile * 2) + 2 * (g.p - g.base);
-        const uint32_t st0 = ring_s + rslot * (KB * G::STAGE_B) + cell;
-#pragma unroll
-        for (int k = 0; k < KB; ++k) {
-            if (k < cnt) {  // warp-uniform
-                const int4 ra = tl[2 * k];
-                const int4 rb = tl[2 * k + 1];
-                const bool first = g.p + k == rb.z || g.p + k == g.lo;  // the user row travels with the first position of a part
-                const bool gi_ = (rb.x >> kPosBits) == 0;               // hot item rows are read from the CTA's cache instead
-                const bool gj_ = C == 2 && (rb.y >> kPosBits) == 0;
-                const uint32_t st = st0 + k * G::STAGE_B;
-                const float* up = ue_l + (size_t)(unsigned)ra.x * (unsigned)D;
-                const float* ip = ie_l + (size_t)(unsigned)ra.z * (unsigned)D;
-                const float* jp = ie_l + (size_t)(unsigned)(C == 2 ? ra.w : 0) * (unsigned)D;
-#pragma unroll
-                for (int v = 0; v < VPL; ++v) {
-                    if (FULL) {
-                        if (first) cp_async16_sf(st + v * 512, up + v * 128);
-                        if (gi_) cp_async16_sf(st + v * 512 + G::ROW_B, ip + v * 128);
-                        if (gj_) cp_async16_sf(st + v * 512 + 2 * G::ROW_B, jp + v * 128);
-                    } else {
-                        const bool ld = (v * 32 + lane) * 4 < D;
-                        const int cc = ld ? v * 128 : -lane * 4;
-                        if (first) cp_async16_s(st + v * 512, up + cc, ld ? 16 : 0);
-                        if (gi_) cp_async16_s(st + v * 512 + G::ROW_B, ip + cc, ld ? 16 : 0);
-                        if (gj_) cp_async16_s(st + v * 512 + 2 * G::ROW_B, jp + cc, ld ? 16 : 0);
-                    }
-                }
-                // lane 0: user bias, lane 1: pos-item bias, lane 2: neg-item bias -- into the lane's own cell
-                const int bi_ = lane == 0 ? ra.x : (lane == 1 ? ra.z : ra.w);
-                if (lane == 0 ? first : bias_lane) cp_async4_s(st - cell + bcell, btab + (unsigned)bi_);
-            }
-        }
-        g.p += cnt;
-    };
-
-    // state of the row part being accumulated (phase 3) -- carried across blocks, never across units
-    float4 ru[VPL], acc[VPL];
-    float uu = 0.f, bu = 0.f, gbias = 0.f;
-    int n_row = 0;
-#pragma unroll
-    for (int v = 0; v < VPL; ++v) ru[v] = acc[v] = f4_zero();
-
-    auto consume = [&](const UnitGen& g, int p0, int cnt, int rslot) {
-        const int4* tl = tiles + g.slot * (kTile * 2) + 2 * (p0 - g.base);  // record of block position k: tl[2k], tl[2k+1]
-        const unsigned char* blk = ring + rslot * (KB * G::STAGE_B);
-        // ---- phase 1: partial dots of the block's positions
-        float dots[KB * C];
+    const int base = (blockIdx.x * kRowWarps + warp) << kUnitShift;
+    if (base < n) {
+        int4(*tl)[2] = s_tile[warp];
         {
-            float4 r1[VPL];
-            float bu1 = bu;
-#pragma unroll
-            for (int v = 0; v < VPL; ++v) r1[v] = ru[v];
-#pragma unroll
-            for (int k = 0; k < KB; ++k) {
-                const bool on = k < cnt;  // positions past the block's end compute on stale data, nothing is kept
-                const int kk = on ? k : 0;
-                const int4 rb = tl[2 * kk + 1];
-                const bool first = on && (p0 + k == rb.z || p0 + k == g.lo);
-                const unsigned char* st = blk + k * G::STAGE_B;
-                const int hi_ = rb.x >> kPosBits, hj_ = C == 2 ? rb.y >> kPosBits : 0;
-                const unsigned char* irow = (hi_ ? cache + (hi_ - 1) * G::ROW_B : st + G::ROW_B) + cell;
-                const unsigned char* jrow = (hj_ ? cache + (hj_ - 1) * G::ROW_B : st + 2 * G::ROW_B) + cell;
-                const float b = *(const float*)(st + bcell);
-                if (first) {
-#pragma unroll
-                    for (int v = 0; v < VPL; ++v) r1[v] = lds4(st + v * 512 + cell);
-                    bu1 = b;  // meaningful on lane 0 only
-                }
-                float dp = 0.f, dn = 0.f;
-#pragma unroll
-                for (int v = 0; v < VPL; ++v) {
-                    dp += f4_dot(r1[v], lds4(irow + v * 512));
-                    if (C == 2) dn += f4_dot(r1[v], lds4(jrow + v * 512));
-                }
-                // every bias enters the score through the lane that copied it
-                const float ub_ = bu1 + bg;
-                dots[C * k] = dp + (lane == 0 ? ub_ : (lane == 1 ? b : 0.f));
-                if (C == 2) dots[C * k + 1] = dn + (lane == 0 ? ub_ : (lane == 2 ? b : 0.f));
+            const int pos = base + lane;
+            const bool ok = lane < kTile && pos < n;
+            if (lane < kTile) {
+                tl[lane][0] = ok ? __ldg(a.pv.s_a + pos) : make_int4(0, 0, 0, 0);
+                tl[lane][1] = ok ? __ldg(a.pv.s_b + pos) : make_int4(0, 0, 0, 0);
             }
         }
-        // ---- phase 2: one reduction, one loss chain per block; lanes [k << KSH, (k+1) << KSH) work on position k
-        float z = transpose_reduce<KB * C>(dots, lane);
-        float zp = z, zn = 0.f;
-        if (C == 2) {
-            const float other = __shfl_xor_sync(BRS_FULL_MASK, z, 1 << (KSH - 1));
-            const bool odd = (lane & (1 << (KSH - 1))) != 0;
-            zp = odd ? other : z;
-            zn = odd ? z : other;
-        }
-        const int kl = lane >> KSH;
-        const bool onl = kl < cnt;
-        const int4 la = tl[2 * (onl ? kl : 0)], lb = tl[2 * (onl ? kl : 0) + 1];
-        const float rating = (C == 1) ? __int_as_float(la.w) : 0.f;
-        float cu_i, cu_j, loss_k;
-        mf_sample_coef_fast<LOSS>(zp, zn, rating, a.inv_b, cu_i, cu_j, loss_k);
-        if (onl && (lane & ((1 << KSH) - 1)) == 0) {
-            loss_acc += loss_k;
-            gb_acc += cu_i + cu_j;
-            const float sf = __int_as_float(la.y);  // hand the coefficients (+ user slot | hot index) to the item stream
-            a.pv.ipair[lb.x & ((1 << kPosBits) - 1)] = make_float2(cu_i, sf);
-            if (C == 2) a.pv.ipair[lb.y & ((1 << kPosBits) - 1)] = make_float2(cu_j, sf);
-        }
-        // ---- phase 3: gradient of the user row
+        __syncwarp();
+        const int lo = snap_cut(base, tl[0][1].z, tl[0][1].w);
+        const int hi = base + kUnit >= n ? n : snap_cut(base + kUnit, tl[kUnit][1].z, tl[kUnit][1].w);
+        // per-lane constants of the gathers
+        const float* ue_l = a.ue.w + lane * 4;
+        const float* ie_l = a.ie.w + lane * 4;
+        const float* btab = lane == 0 ? a.ub.w : a.ib.w;
+        bool colv[VPL];
 #pragma unroll
-        for (int k = 0; k < KB; ++k) {
-            if (k < cnt) {  // warp-uniform
-                const float ci = __shfl_sync(BRS_FULL_MASK, cu_i, k << KSH);
-                const float cj = (C == 2) ? __shfl_sync(BRS_FULL_MASK, cu_j, k << KSH) : 0.f;
-                const int p = p0 + k;
-                const int4 rb = tl[2 * k + 1];
-                const unsigned char* st = blk + k * G::STAGE_B;
-                const int hi_ = rb.x >> kPosBits, hj_ = C == 2 ? rb.y >> kPosBits : 0;
-                const unsigned char* irow = (hi_ ? cache + (hi_ - 1) * G::ROW_B : st + G::ROW_B) + cell;
-                const unsigned char* jrow = (hj_ ? cache + (hj_ - 1) * G::ROW_B : st + 2 * G::ROW_B) + cell;
-                if (p == rb.z || p == g.lo) {  // a new row part starts here: its PRE-step weights stay in registers
-                    uu = 0.f;
+        for (int v = 0; v < VPL; ++v) colv[v] = FULL || (v * 32 + lane) * 4 < D;
+        // state of the row part being accumulated
+        float4 ru[VPL], acc[VPL];
+        float uu = 0.f, bu = 0.f, gbias = 0.f;
+        int n_row = 0;
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) ru[v] = acc[v] = f4_zero();
+
+        for (int p0 = lo; p0 < hi; p0 += K) {  // warp-uniform
+            const int cnt = min(K, hi - p0);
+            const int t0 = p0 - base;
+            // ---- load: every row of the block is in flight before the first one is used
+            float4 ir[K][VPL], jr[C == 2 ? K : 1][VPL], ur[K][VPL];
+            float bb[K];
+            bool first[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                first[k] = false;
+                bb[k] = 0.f;
+#pragma unroll
+                for (int v = 0; v < VPL; ++v) {
+                    ir[k][v] = ur[k][v] = f4_zero();
+                    if (C == 2) jr[k][v] = f4_zero();
+                }
+                if (k < cnt) {  // warp-uniform
+                    const int4 ra = tl[t0 + k][0];
+                    const int sb = tl[t0 + k][1].z;
+                    first[k] = p0 + k == sb || p0 + k == lo;  // the user row is read at the first sample of a part
+                    const float* ip = ie_l + (size_t)(unsigned)ra.z * (unsigned)D;
+                    const float* jp = ie_l + (size_t)(unsigned)(C == 2 ? ra.w : 0) * (unsigned)D;
+                    const float* up = ue_l + (size_t)(unsigned)ra.x * (unsigned)D;
 #pragma unroll
                     for (int v = 0; v < VPL; ++v) {
-                        ru[v] = lds4(st + v * 512 + cell);
-                        uu += f4_dot(ru[v], ru[v]);
-                        acc[v] = f4_zero();
+                        if (colv[v]) {
+                            ir[k][v] = ldg4(ip + v * 128);
+                            if (C == 2) jr[k][v] = ldg4(jp + v * 128);
+                            if (first[k]) ur[k][v] = ldg4(up + v * 128);
+                        }
                     }
-                    bu = *(const float*)(st + bcell);
-                    gbias = 0.f;
-                    n_row = 0;
+                    // lane 0: user bias, lane 1: pos-item bias, lane 2: neg-item bias
+                    const int bi_ = lane == 0 ? ra.x : (lane == 1 ? ra.z : ra.w);
+                    if (lane == 0 ? first[k] : lane <= C) bb[k] = __ldg(btab + (unsigned)bi_);
                 }
+            }
+            // ---- phase 1: partial dots
+            float dots[K * C];
+            {
+                float4 r1[VPL];
+                float bu1 = bu;
 #pragma unroll
-                for (int v = 0; v < VPL; ++v) {
-                    acc[v] = f4_fma(ci, lds4(irow + v * 512), acc[v]);
-                    if (C == 2) acc[v] = f4_fma(cj, lds4(jrow + v * 512), acc[v]);
-                }
-                gbias += ci + cj;
-                n_row += 1;
-                if (p + 1 == rb.w || p + 1 == g.hi) {  // last sample of this row inside my unit
-                    const int4 ra = tl[2 * k];
-                    // regularizer numerator (mf.py:49-54): every forward call of every sample adds |u|^2 + b_u^2
-                    reg_acc += fwd_calls * (float)n_row * (uu + (lane == 0 ? bu * bu : 0.f));
-                    if (a.reg_w != 0.f) {
-                        const float nl = fwd_calls * (float)n_row * rw;
+                for (int v = 0; v < VPL; ++v) r1[v] = ru[v];
 #pragma unroll
-                        for (int v = 0; v < VPL; ++v) acc[v] = f4_fma(nl, ru[v], acc[v]);
-                        gbias += nl * bu;
+                for (int k = 0; k < K; ++k) {
+                    if (first[k]) {
+#pragma unroll
+                        for (int v = 0; v < VPL; ++v) r1[v] = ur[k][v];
+                        bu1 = bb[k];  // meaningful on lane 0 only
                     }
-                    flush_row<VPL, FULL, KIND>(a.ue, a.ub, a.pv.u_ticket, a.u_slot_map, a.user_stage, lane, D, skip, a.release,
-                                               os, ra.y & ((1 << kSlotBits) - 1), ra.x, row_parts(rb.z, rb.w), ru, acc, bu, gbias);
+                    float dp = 0.f, dn = 0.f;
+#pragma unroll
+                    for (int v = 0; v < VPL; ++v) {
+                        dp += f4_dot(r1[v], ir[k][v]);
+                        if (C == 2) dn += f4_dot(r1[v], jr[k][v]);
+                    }
+                    // every bias enters the score through the lane that loaded it
+                    const float ub_ = bu1 + bg;
+                    dots[C * k] = dp + (lane == 0 ? ub_ : (lane == 1 ? bb[k] : 0.f));
+                    if (C == 2) dots[C * k + 1] = dn + (lane == 0 ? ub_ : (lane == 2 ? bb[k] : 0.f));
+                }
+            }
+            // ---- phase 2: one reduction, one loss chain per block; lanes [k << KSH, (k+1) << KSH) work on sample k
+            float z = transpose_reduce<K * C>(dots, lane);
+            float zp = z, zn = 0.f;
+            if (C == 2) {
+                const float other = __shfl_xor_sync(BRS_FULL_MASK, z, 1 << (KSH - 1));
+                const bool odd = (lane & (1 << (KSH - 1))) != 0;
+                zp = odd ? other : z;
+                zn = odd ? z : other;
+            }
+            const int kl = lane >> KSH;
+            const bool onl = kl < cnt;
+            const int4 la = tl[t0 + (onl ? kl : 0)][0], lb = tl[t0 + (onl ? kl : 0)][1];
+            const float rating = (C == 1) ? __int_as_float(la.w) : 0.f;
+            float cu_i, cu_j, loss_k;
+            mf_sample_coef_fast<LOSS>(zp, zn, rating, a.inv_b, cu_i, cu_j, loss_k);
+            if (onl && (lane & ((1 << KSH) - 1)) == 0) {
+                loss_acc += loss_k;
+                gb_acc += cu_i + cu_j;
+                const float sf = __int_as_float(la.y);  // hand the coefficients (+ user slot) to the item stream
+                a.pv.ipair[lb.x] = make_float2(cu_i, sf);
+                if (C == 2) a.pv.ipair[lb.y] = make_float2(cu_j, sf);
+            }
+            // ---- phase 3: gradient of the user row
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                if (k < cnt) {  // warp-uniform
+                    const float ci = __shfl_sync(BRS_FULL_MASK, cu_i, k << KSH);
+                    const float cj = (C == 2) ? __shfl_sync(BRS_FULL_MASK, cu_j, k << KSH) : 0.f;
+                    const int p = p0 + k;
+                    if (first[k]) {  // a new row part starts here: its PRE-step weights stay in registers
+                        uu = 0.f;
+#pragma unroll
+                        for (int v = 0; v < VPL; ++v) {
+                            ru[v] = ur[k][v];
+                            uu += f4_dot(ru[v], ru[v]);
+                            acc[v] = f4_zero();
+                        }
+                        bu = bb[k];
+                        gbias = 0.f;
+                        n_row = 0;
+                    }
+#pragma unroll
+                    for (int v = 0; v < VPL; ++v) {
+                        acc[v] = f4_fma(ci, ir[k][v], acc[v]);
+                        if (C == 2) acc[v] = f4_fma(cj, jr[k][v], acc[v]);
+                    }
+                    gbias += ci + cj;
+                    n_row += 1;
+                    const int4 rb = tl[t0 + k][1];
+                    if (p + 1 == rb.w || p + 1 == hi) {  // last sample of this row inside my unit
+                        const int4 ra = tl[t0 + k][0];
+                        // regularizer numerator (mf.py:49-54): every forward call of every sample adds |u|^2 + b_u^2
+                        reg_acc += fwd_calls * (float)n_row * (uu + (lane == 0 ? bu * bu : 0.f));
+                        if (a.reg_w != 0.f) {
+                            const float nl = fwd_calls * (float)n_row * rw;
+#pragma unroll
+                            for (int v = 0; v < VPL; ++v) acc[v] = f4_fma(nl, ru[v], acc[v]);
+                            gbias += nl * bu;
+                        }
+                        flush_row<VPL, FULL, KIND>(a.ue, a.ub, a.pv.u_ticket, a.u_slot_map, a.user_stage, lane, D, skip,
+                                                   a.release, os, ra.y, ra.x, row_parts(rb.z, rb.w), ru, acc, bu, gbias);
+                    }
                 }
             }
         }
-    };
-
-    // ---- the walk: the issue pointer runs NB - 1 blocks ahead of the consume pointer, across units
-    UnitGen gi, gc;
-    gi.seq = gc.seq = -1;
-    gi.slot = gc.slot = NT - 1;
-    gi.base = gc.base = gi.lo = gc.lo = gi.hi = gc.hi = gi.p = gc.p = 0;
-    gi.valid = gc.valid = true;
-    for (int s = 0; s < PD; ++s) issue_tile(s);
-    cp_async_commit();
-    cp_async_wait<0>();
-    __syncwarp();
-    for (int b = 0; b < NB - 1; ++b) {
-        issue_block(gi, b);
-        cp_async_commit();
     }
-    int cslot = 0, islot = NB - 1;
-    for (;;) {
-        cp_async_wait<NB - 2>();  // the block about to be consumed has landed (this lane's own copies) ...
-        __syncwarp();             // ... and so have the record tiles copied by other lanes; the ring slot
-                                  // consumed last round may be refilled
-        issue_block(gi, islot);
-        cp_async_commit();
-        if (gc.valid && gc.p >= gc.hi) enter(gc, false);
-        if (!gc.valid) break;
-        const int p0 = gc.p, cnt = min(KB, gc.hi - gc.p);
-        gc.p += cnt;
-        consume(gc, p0, cnt, cslot);
-        cslot = cslot + 1 == NB ? 0 : cslot + 1;
-        islot = islot + 1 == NB ? 0 : islot + 1;
-    }
-    cp_async_wait<0>();
-
     // block reduction of the scalar outputs -> 3 atomics per block
     loss_acc = warp_sum(loss_acc);
     reg_acc = warp_sum(reg_acc);
@@ -821,7 +660,7 @@ __global__ void __launch_bounds__(NW * 32) mf_user_rows_kernel(const RowArgs a) 
     if (threadIdx.x == 0 && !skip) {
         float l = 0.f, r = 0.f, g = 0.f;
 #pragma unroll
-        for (int q = 0; q < NW; ++q) {
+        for (int q = 0; q < kRowWarps; ++q) {
             l += s_red[0][q];
             r += s_red[1][q];
             g += s_red[2][q];
@@ -834,17 +673,18 @@ __global__ void __launch_bounds__(NW * 32) mf_user_rows_kernel(const RowArgs a) 
     }
 }
 
-// items kernel: the same walk over the item stream.  Every entry brings the staged PRE-step row of its
-// user; the item's own row (and bias) only travels with the LAST entry of a row part, where the update is
-// applied (and the row's regularizer term is taken).  The last block to finish applies the global-bias
-// step and publishes brs_step_out.
-template <int VPL, bool FULL, int KIND, int NB, int NW, int KB>
-__global__ void __launch_bounds__(NW * 32) mf_item_rows_kernel(const RowArgs a) {
-    using G = RingGeom<VPL, NB, KB, 2, 24>;
-    constexpr int NT = G::NT, PD = G::PD;
-    extern __shared__ __align__(16) unsigned char smem[];
+// items kernel: one warp per work unit of the item stream -- a row-per-warp SpMM over the batch's
+// (coefficient, user slot) entries: 8 staged PRE-step user rows in flight per warp, the item's gradient in
+// registers; at the end of a row part the item's own row and bias are read, the regularizer term taken and
+// the update applied in place.  The last block to finish applies the global-bias step and publishes
+// brs_step_out.
+template <int VPL, bool FULL, int KIND>
+__global__ void __launch_bounds__(kRowThreads) mf_item_rows_kernel(const RowArgs a) {
+    constexpr int K = 8;
+    __shared__ int4 s_ia[kRowWarps][kTile];    // i_a of stream position base + t
+    __shared__ float2 s_pr[kRowWarps][kTile];  // {coefficient, user slot}
     __shared__ OptScalars s_opt;
-    __shared__ float s_red[NW];
+    __shared__ float s_red[kRowWarps];
     __shared__ bool s_last;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -855,191 +695,106 @@ __global__ void __launch_bounds__(NW * 32) mf_item_rows_kernel(const RowArgs a) 
     const bool skip = __ldg(a.err) != 0u;
     const int n = __ldg(a.pv.hdr + 1);
     const float rw = 2.0f * a.reg_w * a.inv_b;
-    const int W = gridDim.x * NW;
-    const int gw = warp * gridDim.x + blockIdx.x;
     float reg_acc = 0.f;
-
-    unsigned char* wbase = smem + (size_t)warp * G::WARP_B;
-    // tile s: kTile records i_a (16 bytes each), then kTile pairs {coefficient, user slot} (8 bytes each)
-    auto tile_a = [&](int slot) { return (const int4*)(wbase + slot * G::TILE_B); };
-    auto tile_p = [&](int slot) { return (const float2*)(wbase + slot * G::TILE_B + kTile * 16); };
-    unsigned char* ring = wbase + NT * G::TILE_B;
-    const uint32_t tiles_s = smem_u32(wbase), ring_s = smem_u32(ring);
-    const int cell = lane * 16;
-    const int bcell = G::BIAS_OFF;  // lane 0's cell
-    const float* us_l = a.user_stage + lane * 4;
-    const float* ie_l = a.ie.w + lane * 4;
-    // the staged PRE-step rows of the batch's hot users -> shared memory, once per CTA
-    const unsigned char* cache = smem + NW * G::WARP_B;
-    {
-        const int nh = min(__ldg(a.pv.hdr + 4), kHotRows);
-        for (int h = warp; h < nh; h += NW) {
-            const float* src = us_l + (size_t)(unsigned)__ldg(a.pv.u_hotlist + h) * (unsigned)D;
-#pragma unroll
-            for (int v = 0; v < VPL; ++v) {
-                const bool ld = FULL || (v * 32 + lane) * 4 < D;
-                *(float4*)(smem + NW * G::WARP_B + h * G::ROW_B + v * 512 + cell) = ld ? ld4(src + v * 128) : f4_zero();
+    const int base = (blockIdx.x * kRowWarps + warp) << kUnitShift;
+    if (base < n) {
+        int4* ta = s_ia[warp];
+        float2* tp = s_pr[warp];
+        {
+            const int pos = base + lane;
+            const bool ok = lane < kTile && pos < n;
+            if (lane < kTile) {
+                ta[lane] = ok ? __ldg(a.pv.i_a + pos) : make_int4(0, 0, 0, 0);
+                tp[lane] = ok ? __ldcg(a.pv.ipair + pos) : make_float2(0.f, 0.f);
             }
         }
-        __syncthreads();
-    }
+        __syncwarp();
+        const int lo = snap_cut(base, ta[0].z, ta[0].w);
+        const int hi = base + kUnit >= n ? n : snap_cut(base + kUnit, ta[kUnit].z, ta[kUnit].w);
+        const float* us_l = a.user_stage + lane * 4;
+        const float* ie_l = a.ie.w + lane * 4;
+        bool colv[VPL];
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) colv[v] = FULL || (v * 32 + lane) * 4 < D;
+        float4 acc[VPL];
+        float gbias = 0.f;
+        int n_row = 0;
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) acc[v] = f4_zero();
 
-    auto issue_tile = [&](int seq) {
-        const int pos = ((gw + seq * W) << kUnitShift) + lane;
-        const bool ok = lane < kTile && pos < n;
-        const uint32_t tl = tiles_s + (seq % NT) * G::TILE_B;
-        if (lane < kTile) {
-            cp_async16_s(tl + lane * 16, a.pv.i_a + (ok ? pos : 0), ok ? 16 : 0);
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(tl + kTile * 16 + lane * 8),
-                         "l"(a.pv.ipair + (ok ? pos : 0)), "r"(ok ? 8 : 0)
-                         : "memory");
-        }
-    };
-    auto enter = [&](UnitGen& g, bool prefetch) {
-        for (;;) {
-            g.seq += 1;
-            g.slot = g.slot + 1 == NT ? 0 : g.slot + 1;
-            if (prefetch) issue_tile(g.seq + PD);
-            const int base = (gw + g.seq * W) << kUnitShift;
-            if (base >= n) {
-                g.valid = false;
-                return;
-            }
-            const int4* tl = tile_a(g.slot);
-            const int4 r0 = tl[0], r1 = tl[kUnit];
-            g.base = base;
-            g.lo = snap_cut(base, r0.z, r0.w);
-            g.hi = base + kUnit >= n ? n : snap_cut(base + kUnit, r1.z, r1.w);
-            g.p = g.lo;
-            if (g.lo < g.hi) return;
-        }
-    };
-    auto issue_block = [&](UnitGen& g, int rslot) {
-        if (g.valid && g.p >= g.hi) enter(g, true);
-        if (!g.valid) return;
-        const int cnt = min(KB, g.hi - g.p);
-        const int4* ta = tile_a(g.slot) + (g.p - g.base);
-        const float2* tp = tile_p(g.slot) + (g.p - g.base);
-        const uint32_t st0 = ring_s + rslot * (KB * G::STAGE_B) + cell;
+        for (int q0 = lo; q0 < hi; q0 += K) {  // warp-uniform
+            const int cnt = min(K, hi - q0);
+            const int t0 = q0 - base;
+            // every row of the block is in flight before the first one is used: the staged user row of each
+            // entry and, where a row part ends, the item's own row and bias (no dependent load at the flush)
+            float4 rr[K][VPL], wr[K][VPL];
+            float wb[K];
 #pragma unroll
-        for (int k = 0; k < KB; ++k) {
-            if (k < cnt) {  // warp-uniform
-                const int q = g.p + k;
-                const int4 ia = ta[k];
-                const int usy = __float_as_int(tp[k].y);
-                const int us = usy & ((1 << kSlotBits) - 1);
-                const bool gu_ = (usy >> kSlotBits) == 0;  // hot users' rows are read from the CTA's cache instead
-                const bool last = q + 1 == ia.w || q + 1 == g.hi;
-                const uint32_t st = st0 + k * G::STAGE_B;
-                const float* up = us_l + (size_t)(unsigned)us * (unsigned)D;
-                const float* ip = ie_l + (size_t)(unsigned)ia.x * (unsigned)D;
+            for (int k = 0; k < K; ++k) {
+                wb[k] = 0.f;
 #pragma unroll
-                for (int v = 0; v < VPL; ++v) {
-                    if (FULL) {
-                        if (gu_) cp_async16_sf(st + v * 512, up + v * 128);
-                        if (last) cp_async16_sf(st + v * 512 + G::ROW_B, ip + v * 128);
-                    } else {
-                        const bool ld = (v * 32 + lane) * 4 < D;
-                        const int cc = ld ? v * 128 : -lane * 4;
-                        if (gu_) cp_async16_s(st + v * 512, up + cc, ld ? 16 : 0);
-                        if (last) cp_async16_s(st + v * 512 + G::ROW_B, ip + cc, ld ? 16 : 0);
-                    }
-                }
-                if (last && lane == 0) cp_async4_s(st + bcell, a.ib.w + (unsigned)ia.x);
-            }
-        }
-        g.p += cnt;
-    };
-
-    float4 acc[VPL];
-    float gbias = 0.f;
-    int n_row = 0;
-#pragma unroll
-    for (int v = 0; v < VPL; ++v) acc[v] = f4_zero();
-
-    auto consume = [&](const UnitGen& g, int q0, int cnt, int rslot) {
-        const int4* ta = tile_a(g.slot) + (q0 - g.base);
-        const float2* tp = tile_p(g.slot) + (q0 - g.base);
-        const unsigned char* blk = ring + rslot * (KB * G::STAGE_B);
-#pragma unroll
-        for (int k = 0; k < KB; ++k) {
-            if (k < cnt) {  // warp-uniform
-                const int q = q0 + k;
-                const int4 ia = ta[k];
-                const float2 pr = tp[k];
-                const float coef = pr.x;
-                const int hu_ = __float_as_int(pr.y) >> kSlotBits;
-                const unsigned char* st = blk + k * G::STAGE_B;
-                const unsigned char* urow = (hu_ ? cache + (hu_ - 1) * G::ROW_B : st) + cell;
-                if (q == ia.z || q == g.lo) {
-#pragma unroll
-                    for (int v = 0; v < VPL; ++v) acc[v] = f4_zero();
-                    gbias = 0.f;
-                    n_row = 0;
-                }
-#pragma unroll
-                for (int v = 0; v < VPL; ++v) acc[v] = f4_fma(coef, lds4(urow + v * 512), acc[v]);
-                gbias += coef;
-                n_row += 1;
-                if (q + 1 == ia.w || q + 1 == g.hi) {
-                    float4 w[VPL];
-                    float ww = 0.f;
+                for (int v = 0; v < VPL; ++v) rr[k][v] = wr[k][v] = f4_zero();
+                if (k < cnt) {  // warp-uniform
+                    const float* up = us_l + (size_t)(unsigned)__float_as_int(tp[t0 + k].y) * (unsigned)D;
+                    const int4 ia = ta[t0 + k];
+                    const bool last = q0 + k + 1 == ia.w || q0 + k + 1 == hi;
+                    const float* ip = ie_l + (size_t)(unsigned)ia.x * (unsigned)D;
 #pragma unroll
                     for (int v = 0; v < VPL; ++v) {
-                        w[v] = lds4(st + G::ROW_B + v * 512 + cell);
-                        ww += f4_dot(w[v], w[v]);
+                        if (colv[v]) {
+                            rr[k][v] = ldg4(up + v * 128);
+                            if (last) wr[k][v] = ld4(ip + v * 128);
+                        }
                     }
-                    const float bi = *(const float*)(st + bcell);
-                    reg_acc += (float)n_row * (ww + (lane == 0 ? bi * bi : 0.f));  // mf.py:49-54, item side
-                    if (a.reg_w != 0.f) {
-                        const float nl = (float)n_row * rw;
+                    if (last) wb[k] = a.ib.w[(unsigned)ia.x];
+                }
+            }
 #pragma unroll
-                        for (int v = 0; v < VPL; ++v) acc[v] = f4_fma(nl, w[v], acc[v]);
-                        gbias += nl * bi;
+            for (int k = 0; k < K; ++k) {
+                if (k < cnt) {  // warp-uniform
+                    const int q = q0 + k;
+                    const int4 ia = ta[t0 + k];
+                    const float coef = tp[t0 + k].x;
+                    if (q == ia.z || q == lo) {
+#pragma unroll
+                        for (int v = 0; v < VPL; ++v) acc[v] = f4_zero();
+                        gbias = 0.f;
+                        n_row = 0;
                     }
-                    flush_row<VPL, FULL, KIND>(a.ie, a.ib, a.pv.i_ticket, a.i_slot_map, nullptr, lane, D, skip, a.release, os,
-                                               ia.y, ia.x, row_parts(ia.z, ia.w), w, acc, bi, gbias);
+#pragma unroll
+                    for (int v = 0; v < VPL; ++v) acc[v] = f4_fma(coef, rr[k][v], acc[v]);
+                    gbias += coef;
+                    n_row += 1;
+                    if (q + 1 == ia.w || q + 1 == hi) {
+                        float4 w[VPL];
+                        float ww = 0.f;
+#pragma unroll
+                        for (int v = 0; v < VPL; ++v) {
+                            w[v] = wr[k][v];
+                            ww += f4_dot(w[v], w[v]);
+                        }
+                        const float bi = wb[k];
+                        reg_acc += (float)n_row * (ww + (lane == 0 ? bi * bi : 0.f));  // mf.py:49-54, item side
+                        if (a.reg_w != 0.f) {
+                            const float nl = (float)n_row * rw;
+#pragma unroll
+                            for (int v = 0; v < VPL; ++v) acc[v] = f4_fma(nl, w[v], acc[v]);
+                            gbias += nl * bi;
+                        }
+                        flush_row<VPL, FULL, KIND>(a.ie, a.ib, a.pv.i_ticket, a.i_slot_map, nullptr, lane, D, skip, a.release,
+                                                   os, ia.y, ia.x, row_parts(ia.z, ia.w), w, acc, bi, gbias);
+                    }
                 }
             }
         }
-    };
-
-    UnitGen gi, gc;
-    gi.seq = gc.seq = -1;
-    gi.slot = gc.slot = NT - 1;
-    gi.base = gc.base = gi.lo = gc.lo = gi.hi = gc.hi = gi.p = gc.p = 0;
-    gi.valid = gc.valid = true;
-    for (int s = 0; s < PD; ++s) issue_tile(s);
-    cp_async_commit();
-    cp_async_wait<0>();
-    __syncwarp();
-    for (int b = 0; b < NB - 1; ++b) {
-        issue_block(gi, b);
-        cp_async_commit();
     }
-    int cslot = 0, islot = NB - 1;
-    for (;;) {
-        cp_async_wait<NB - 2>();
-        __syncwarp();
-        issue_block(gi, islot);
-        cp_async_commit();
-        if (gc.valid && gc.p >= gc.hi) enter(gc, false);
-        if (!gc.valid) break;
-        const int q0 = gc.p, cnt = min(KB, gc.hi - gc.p);
-        gc.p += cnt;
-        consume(gc, q0, cnt, cslot);
-        cslot = cslot + 1 == NB ? 0 : cslot + 1;
-        islot = islot + 1 == NB ? 0 : islot + 1;
-    }
-    cp_async_wait<0>();
-
     reg_acc = warp_sum(reg_acc);
     if (lane == 0) s_red[warp] = reg_acc;
     __syncthreads();
     if (threadIdx.x == 0 && !skip) {
         float r = 0.f;
 #pragma unroll
-        for (int q = 0; q < NW; ++q) r += s_red[q];
+        for (int q = 0; q < kRowWarps; ++q) r += s_red[q];
         if (r != 0.f) atomicAdd(&a.ws->reg_sum, (double)r);
     }
     if (!a.finalize) return;
@@ -1078,27 +833,6 @@ __global__ void __launch_bounds__(NW * 32) mf_item_rows_kernel(const RowArgs a) 
     *a.i_count = 0;
 }
 
-// The rings and the hot-row cache live in shared memory, which is carved out of the same 228 KB as L1; the
-// hot rows no longer depend on L1, so the CTAs may take most of the array.
-int g_rows_blocks_per_sm = 0;  // 0 = default below; diagnostics: brs_debug_set_mf_rows_shape
-template <class K>
-int launch_persistent(K kernel, int threads, int smem_bytes, const RowArgs& a, cudaStream_t st) {
-    BRS_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    BRS_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    int per_sm = 1;
-    BRS_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, (size_t)smem_bytes));
-    if (per_sm < 1) per_sm = 1;
-    int want = g_rows_blocks_per_sm > 0 ? g_rows_blocks_per_sm : (210 * 1024) / (smem_bytes + 1024);
-    if (want < 1) want = 1;
-    if (per_sm > want) per_sm = want;
-    // ask for the smallest carve-out that holds per_sm blocks; the rest of the 228 KB is L1
-    int pct = (int)(((long long)per_sm * (smem_bytes + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024));
-    if (pct > 100) pct = 100;
-    BRS_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
-    kernel<<<brs_sm_count() * per_sm, threads, smem_bytes, st>>>(a);
-    return BRS_OK;
-}
-
 int check_model(const brs_mf_model* m, int which) {
     if (!m || !m->ws || which < 0 || which > 1) return BRS_ERR_INVALID_ARG;
     if (m->user.n_tables < 2 || m->item.n_tables < 2) return BRS_ERR_INVALID_ARG;
@@ -1121,38 +855,47 @@ int check_model(const brs_mf_model* m, int which) {
     return BRS_OK;
 }
 
-int g_rows_blocks = 2, g_rows_warps = 8, g_rows_kb = 2;  // ring blocks per warp / warps per CTA / positions per block
-int g_rows_only = 0;                                     // diagnostics: 1 = users kernel only, 2 = items kernel only
+
+int g_rows_only = 0;  // diagnostics: 1 = users kernel only, 2 = items kernel only
+
+template <class K>
+int launch_units(K kernel, long long max_positions, const RowArgs& a, cudaStream_t st) {
+    // the kernels keep their rows in registers and lean on L1 for the Zipf-hot rows: a carve-out that just holds
+    // the record tiles of the CTAs the register file admits (<= 4 x 8.3 KB), the rest of the array stays L1
+    static bool configured[16] = {};  // per kernel instantiation and device: keep driver calls off the per-step path
+    int dev = 0;
+    BRS_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 16 || !configured[dev]) {
+        BRS_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 20));
+        if (dev >= 0 && dev < 16) configured[dev] = true;
+    }
+    const long long units = (max_positions + kUnit - 1) >> kUnitShift;
+    long long blocks = (units + kRowWarps - 1) / kRowWarps;
+    if (blocks < 1) blocks = 1;  // the items kernel's last block finalises the step even for an empty batch
+    kernel<<<(unsigned)blocks, kRowThreads, 0, st>>>(a);
+    return BRS_OK;
+}
 
 template <int LOSS, int KIND>
-int launch_rows(const RowArgs& a, cudaStream_t st) {
+int launch_rows(const RowArgs& a, long long batch, cudaStream_t st) {
     const int D = a.dim;
-#define BRS_ROWS_SN(VPL, FULL, NB, NW, KB)                                                                  \
-    do {                                                                                                    \
-        int rc_ = BRS_OK;                                                                                   \
-        if (g_rows_only != 2)                                                                               \
-            rc_ = launch_persistent(mf_user_rows_kernel<VPL, FULL, LOSS, KIND, NB, NW, KB>, NW * 32,        \
-                                    NW * RingGeom<VPL, NB, KB, 3, 32>::WARP_B + RingGeom<VPL, NB, KB, 3, 32>::CACHE_B, a, st); \
-        if (rc_ != BRS_OK) return rc_;                                                                      \
-        if (g_rows_only != 1)                                                                               \
-            rc_ = launch_persistent(mf_item_rows_kernel<VPL, FULL, KIND, NB, NW, KB>, NW * 32,              \
-                                    NW * RingGeom<VPL, NB, KB, 2, 24>::WARP_B + RingGeom<VPL, NB, KB, 2, 24>::CACHE_B, a, st); \
-        if (rc_ != BRS_OK) return rc_;                                                                      \
+    const long long n_u = batch, n_i = (LOSS == LOSS_BPR ? 2 : 1) * batch;  // upper bounds of the stream lengths
+#define BRS_ROWS(VPL, FULL)                                                                      \
+    do {                                                                                         \
+        int rc_ = BRS_OK;                                                                        \
+        if (g_rows_only != 2) rc_ = launch_units(mf_user_rows_kernel<VPL, FULL, LOSS, KIND>, n_u, a, st); \
+        if (rc_ != BRS_OK) return rc_;                                                           \
+        if (g_rows_only != 1) rc_ = launch_units(mf_item_rows_kernel<VPL, FULL, KIND>, n_i, a, st);       \
+        if (rc_ != BRS_OK) return rc_;                                                           \
     } while (0)
     // a row of D floats = 32 lanes x VPL float4 (lanes past dim idle for dim < 128)
-    if (D == 128 && (g_rows_blocks != 2 || g_rows_warps != 8 || g_rows_kb != 2)) {  // tuning sweep of the benchmark shape
-        if (g_rows_blocks == 2 && g_rows_warps == 4 && g_rows_kb == 2) BRS_ROWS_SN(1, true, 2, 4, 2);
-        else if (g_rows_blocks == 2 && g_rows_warps == 16 && g_rows_kb == 2) BRS_ROWS_SN(1, true, 2, 16, 2);
-        else if (g_rows_blocks == 2 && g_rows_warps == 8 && g_rows_kb == 4) BRS_ROWS_SN(1, true, 2, 8, 4);
-        else if (g_rows_blocks == 3 && g_rows_warps == 8 && g_rows_kb == 2) BRS_ROWS_SN(1, true, 3, 8, 2);
-        else return BRS_ERR_INVALID_ARG;
-    } else if (D == 128) BRS_ROWS_SN(1, true, 2, 8, 2);
-    else if (D < 128) BRS_ROWS_SN(1, false, 2, 8, 2);
-    else if (D == 256) BRS_ROWS_SN(2, true, 2, 4, 2);
-    else if (D < 256) BRS_ROWS_SN(2, false, 2, 4, 2);
-    else if (D <= 384) BRS_ROWS_SN(3, false, 2, 2, 2);
-    else BRS_ROWS_SN(4, false, 2, 2, 2);
-#undef BRS_ROWS_SN
+    if (D == 128) BRS_ROWS(1, true);
+    else if (D < 128) BRS_ROWS(1, false);
+    else if (D == 256) BRS_ROWS(2, true);
+    else if (D < 256) BRS_ROWS(2, false);
+    else if (D <= 384) BRS_ROWS(3, false);
+    else BRS_ROWS(4, false);
+#undef BRS_ROWS
     BRS_CUDA_CHECK(cudaGetLastError());
     return BRS_OK;
 }
@@ -1168,15 +911,6 @@ extern "C" int64_t brs_mf_plan_bytes(int64_t batch_capacity, int32_t user_capaci
 
 extern "C" int brs_debug_set_mf_rows_only(int which) {
     g_rows_only = which;
-    return BRS_OK;
-}
-
-extern "C" int brs_debug_set_mf_rows_shape(int ring_blocks, int warps_per_block, int blocks_per_sm, int block_positions) {
-    if (ring_blocks < 2 || ring_blocks > 3 || (block_positions != 2 && block_positions != 4)) return BRS_ERR_INVALID_ARG;
-    g_rows_kb = block_positions;
-    g_rows_blocks = ring_blocks;
-    g_rows_warps = warps_per_block;
-    g_rows_blocks_per_sm = blocks_per_sm;
     return BRS_OK;
 }
 
@@ -1197,8 +931,6 @@ extern "C" int brs_mf_plan_build(const brs_mf_model* model, int32_t which, int32
     a.third = third;
     a.batch = batch;
     a.n_cols = loss_kind == LOSS_BPR ? 2 : 1;
-    // the hot index travels in the spare high bits of slots / stream positions
-    a.hot_reads = (pl.user_capacity < (1 << kSlotBits) && 2 * batch < (1ll << kPosBits) - 1) ? kHotReads : 0x7fffffff;
     a.err = &((brs_step_ws*)model->ws)->err_pending[which];
     cudaStream_t st = (cudaStream_t)stream;
     if (batch > 0) {
@@ -1277,7 +1009,7 @@ extern "C" int brs_mf_step_planned(const brs_mf_model* model, int32_t which, con
     a.inv_batch = batch > 0 ? 1.0 / (double)batch : 0.0;
     cudaStream_t st = (cudaStream_t)stream;
 #define BRS_STEP(KIND)                                            \
-    (loss_kind == LOSS_BPR ? launch_rows<LOSS_BPR, KIND>(a, st) : launch_rows<LOSS_BCE, KIND>(a, st))
+    (loss_kind == LOSS_BPR ? launch_rows<LOSS_BPR, KIND>(a, batch, st) : launch_rows<LOSS_BCE, KIND>(a, batch, st))
     switch (opt->kind) {
         case BRS_SGD: rc = BRS_STEP(BRS_SGD); break;
         case BRS_ADAM: rc = BRS_STEP(BRS_ADAM); break;

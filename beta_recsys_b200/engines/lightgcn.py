@@ -112,11 +112,17 @@ class LightGCNEngine(ModelEngine):
         self._all[m.n_users:].copy_(m.item_embedding.weight.data)
         m.user_embedding.weight.data = self._all[: m.n_users]
         m.item_embedding.weight.data = self._all[m.n_users:]
-        adj = self.norm_adj.coalesce()
-        idx = adj.indices().cpu().numpy()
-        csr = coo_to_csr(idx[0], idx[1], adj.values().cpu().numpy(), n)
-        self._nnz = csr["nnz"]
-        self._csr = {k: torch.from_numpy(v).to(dev) for k, v in csr.items() if k != "nnz"}
+        if hasattr(self.norm_adj, "csr_tensors"):  # graph.GpuAdjacency: built on the device, nothing to convert
+            if self.norm_adj.n != n:
+                raise ValueError("norm_adj is %d x %d, the model has %d nodes" % (self.norm_adj.n, self.norm_adj.n, n))
+            self._nnz = self.norm_adj.nnz
+            self._csr = {k: v.to(dev) for k, v in self.norm_adj.csr_tensors().items()}
+        else:  # the reference's torch sparse tensor (recommenders/lightgcn.py:15-23)
+            adj = self.norm_adj.coalesce()
+            idx = adj.indices().cpu().numpy()
+            csr = coo_to_csr(idx[0], idx[1], adj.values().cpu().numpy(), n)
+            self._nnz = csr["nnz"]
+            self._csr = {k: torch.from_numpy(v).to(dev) for k, v in csr.items() if k != "nnz"}
         self._layers = [self._all] + [torch.zeros((n, d), dtype=torch.float32, device=dev) for _ in range(m.n_layers)]
         self._d = torch.zeros((n, d), dtype=torch.float32, device=dev)
         self._g = [torch.zeros((n, d), dtype=torch.float32, device=dev) for _ in range(2)]

@@ -58,7 +58,7 @@ class MF(nn.Module):
         return self._engine.scores(users_t, items_t)
 
 
-DEFAULT_STEP_IMPL = "scratch"
+DEFAULT_STEP_IMPL = "rows"
 
 
 class MFEngine(ModelEngine):
@@ -90,8 +90,8 @@ class MFEngine(ModelEngine):
         self._gb_state = opt.add_param("global_bias", m.global_bias.data)
         self._ws = torch.zeros(_lib.STEP_WS_BYTES, dtype=torch.uint8, device=dev)
         self._out = torch.zeros(4, dtype=torch.float32, device=dev)
-        # "scratch" (default): fused gather/loss/RED kernel + gradient-scratch apply (csrc/mf_kernels.cu,
-        # rows_apply.cu); "rows": the row-owner step of csrc/mf_rowwise.cu (second implementation, same results)
+        # "rows" (default): the row-owner step of csrc/mf_rowwise.cu; "scratch": round 1's fused gather/loss/RED
+        # kernel + gradient-scratch apply (csrc/mf_kernels.cu, rows_apply.cu), kept as a second implementation
         mc = self.config["model"]
         self._step_impl = mc["step_impl"] if "step_impl" in mc else DEFAULT_STEP_IMPL
         if self._step_impl not in ("rows", "scratch"):

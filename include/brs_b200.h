@@ -251,10 +251,6 @@ int brs_mf_step(const brs_mf_model *model, const brs_opt *opt, int32_t loss_kind
                 const int64_t *items, const void *third, int64_t batch, float reg_weight,
                 float *out /* brs_step_out */, void *stream);
 
-/* diagnostics: ring blocks per warp (2 | 3), warps per CTA (2 | 4 | 8) of the two row kernels (dim 128
- * only), the cap on resident CTAs per SM (0 = default: the rings leave L1 a share of the array) and the
- * stream positions per block (2 | 4) */
-int brs_debug_set_mf_rows_shape(int ring_blocks, int warps_per_block, int blocks_per_sm, int block_positions);
 /* diagnostics (per-kernel timing on a FIXED plan; leaves the step incomplete): 0 = both row kernels,
  * 1 = users kernel only, 2 = items kernel only */
 int brs_debug_set_mf_rows_only(int which);
@@ -532,6 +528,23 @@ int brs_pairset_build(const int64_t *users, const int64_t *items, int64_t n, int
 int brs_sample_negatives(const void *set, int64_t n_pairs_in_set, const int64_t *users, int64_t n, int64_t n_items,
                          int32_t num_negative, uint64_t seed, int64_t *neg_out, void *stream);
 int brs_pairset_status(const void *set, uint32_t *status_out, void *stream);
+
+/* ---- normalised adjacency: BaseData.create_adj_mat (beta_rec/data/base_data.py:337-360) + normalized_adj_single
+ * (beta_rec/utils/common_util.py:24-41) ----
+ * Interactions (users[e], items[e]) -> CSR of norm_adj = D^-1 (A + I) (self_loops = 1) or mean_adj = D^-1 A
+ * (self_loops = 0) over the n_users + n_items nodes, A = [[0, R], [R^T, 0]], R[u, i] = 1 (duplicates collapse);
+ * rows and columns in coalesced order, values fp32(1.0 / rowsum) with the division in float64 like the reference.
+ * The pattern is symmetric, so the transpose shares row_ptr / col: val_t holds its values and edge_id_t maps each
+ * transposed non-zero to its forward edge (what brs_spmm_csr's backward and the dropout mask need).
+ * Outputs (device): row_ptr int32 [n + 1]; col, val, val_t, edge_id_t sized for the bound 2 * n_interactions + n;
+ * nnz_out int64 [1] = entries actually written.  2 * n_interactions + n < 2^31.  Sorting is cub::DeviceRadixSort
+ * (library plumbing; this runs once per training run).  brs_adj_status (synchronises): 1 = an id out of range. */
+int64_t brs_adj_workspace_bytes(int64_t n_interactions, int64_t n_users, int64_t n_items);
+int brs_adj_build(const int64_t *users, const int64_t *items, int64_t n_interactions, int64_t n_users, int64_t n_items,
+                  int32_t self_loops, void *workspace, int64_t workspace_bytes, int32_t *row_ptr, int32_t *col, float *val,
+                  float *val_t, int32_t *edge_id_t, int64_t *nnz_out, void *stream);
+int brs_adj_status(const void *workspace, int64_t n_interactions, int64_t n_users, int64_t n_items, uint32_t *status_out,
+                   void *stream);
 
 #ifdef __cplusplus
 }

@@ -82,7 +82,7 @@ def test_bpr_loader_feeds_train_an_epoch_like_the_reference_loader():
     for b in order:
         O.mf_train_single_batch(p, st, tuple(c[b] for c in cols), "bpr", "sgd", 0.05, 0.0)
     for k, v in eng.model.state_dict().items():
-        # the global bias starts at 0 and sums 2B opposite-sign terms per step: absolute budget (cf. test_mf_gpu.Scale)
-        scale = max(np.abs(p[k]).max(), 1e-2 if k == "global_bias" else 1e-30)
+        # the biases start at 0 and sum opposite-sign terms: absolute budget for them (cf. test_mf_gpu.Scale)
+        scale = max(np.abs(p[k]).max(), 1e-2)
         err = np.abs(v.cpu().numpy() - p[k]).max() / scale
         assert err <= 1e-5, (k, err)

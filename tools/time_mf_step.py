@@ -32,7 +32,7 @@ def make(a, impl):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--impl", nargs="+", default=["rows", "scratch"])
-    ap.add_argument("--shape", nargs="+", default=["2,8,0,2"], help="rows kernels: ring_blocks,warps_per_block,blocks_per_sm,block_positions")
+    ap.add_argument("--shape", nargs="+", default=["-"], help="unused (kept for old command lines)")
     ap.add_argument("--opt", default="sgd")
     ap.add_argument("--adam-mode", default="touched")
     ap.add_argument("--users", type=int, default=1_000_000)
@@ -70,9 +70,7 @@ def main():
         torch.cuda.empty_cache()
 
     for impl in a.impl:
-        for shape in (a.shape if impl == "rows" else ["0,0,0,2"]):
-            if impl == "rows":
-                _lib.check(lib.brs_debug_set_mf_rows_shape(*[int(x) for x in shape.split(",")]))
+        for shape in ["-"]:
             eng = make(a, impl)
             out = torch.empty((a.nb, 4), dtype=torch.float32, device=dev)
 
