@@ -1,6 +1,7 @@
 // Device helpers shared by the sm_100a kernels of libbrs_b200.so.
 #pragma once
 #include <cuda_runtime.h>
+#include <stddef.h>
 #include <stdint.h>
 
 #include "../../include/brs_b200.h"
@@ -17,8 +18,12 @@ struct __align__(16) brs_step_ws {
     long long step;           // optimizer step counter t (incremented by apply)
     unsigned int err_flag;    // set when an index is out of range
     unsigned int err_pending[2];  // same, raised by a pre-pass that ran inside the PREVIOUS step's apply launch
-    unsigned int pad_[7];
+    unsigned int predict_err; // raised by the no_grad scoring kernels only (never by a training step): the
+                              // host reads and clears it after a predict call (engines: _check_predict)
+    unsigned int pad_[6];
 };
+#define BRS_WS_PREDICT_ERR_OFFSET 44
+static_assert(offsetof(brs_step_ws, predict_err) == BRS_WS_PREDICT_ERR_OFFSET, "engines read this word through the ws tensor");
 static_assert(sizeof(brs_step_ws) <= BRS_STEP_WS_BYTES, "ws layout");
 
 // ---------------------------------------------------------------------------
@@ -112,6 +117,18 @@ __device__ __forceinline__ void red_add4(float* p, float4 v) {
 }
 __device__ __forceinline__ void red_add1(float* p, float v) {
     asm volatile("red.relaxed.gpu.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+
+// The same reductions at SYSTEM scope, for destinations that may be another GPU's memory (row-sharded push:
+// up to 8 GPUs reduce into the same hot rows over NVLink).  At .gpu scope those cross-device reductions are
+// not morally strong under the PTX memory model.
+__device__ __forceinline__ void red_add4_sys(float* p, float4 v) {
+    asm volatile("red.relaxed.sys.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+                 "f"(v.w)
+                 : "memory");
+}
+__device__ __forceinline__ void red_add1_sys(float* p, float v) {
+    asm volatile("red.relaxed.sys.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

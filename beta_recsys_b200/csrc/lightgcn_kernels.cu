@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(kThreads) lightgcn_tail_kernel(const TailArgs 
         bool ok = true;
         if ((unsigned long long)u >= (unsigned long long)a.n_users || (unsigned long long)i >= (unsigned long long)a.n_items ||
             (unsigned long long)j >= (unsigned long long)a.n_items) {
-            if (lane == 0) atomicOr(&a.ws->err_flag, 1u);
+            if (lane == 0) atomicOr(a.train ? &a.ws->err_flag : &a.ws->predict_err, 1u);
             ok = false;
             u = i = j = 0;
         }

@@ -384,7 +384,12 @@ __global__ void __launch_bounds__(kThreads) mf_predict_kernel(const float* __res
         bool valid = s < n;
         long long u = valid ? users[s] : 0, i = valid ? items[s] : 0;
         if ((unsigned long long)u >= (unsigned long long)n_users || (unsigned long long)i >= (unsigned long long)n_items) {
-            if (valid && gl == 0) atomicOr(err, 1u);
+            // the reference raises IndexError inside nn.Embedding: flag it in the predict-only error word and
+            // publish NaN for the sample (nothing is left uninitialised)
+            if (valid && gl == 0) {
+                atomicOr(err, 1u);
+                scores[s] = __int_as_float(0x7fc00000);
+            }
             valid = false;
             u = i = 0;
         }
@@ -575,7 +580,7 @@ extern "C" int brs_mf_predict(const brs_mf_model* model, const int64_t* users, c
     const int D = a.dim;
     if (D % 4 != 0 || D <= 0 || D > 512) return BRS_ERR_UNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
-    unsigned int* err = &a.ws->err_flag;
+    unsigned int* err = &a.ws->predict_err;
 #define BRS_PRED(LPR, VPL, FULL)                                                                                   \
     do {                                                                                                           \
         auto k = mf_predict_kernel<LPR, VPL, FULL>;                                                                \
@@ -712,15 +717,15 @@ __global__ void __launch_bounds__(256) mf_push_kernel(const PushArgs a) {
             float* src = a.scratch_emb[e] + gs_off(D, rs.capacity, (unsigned)s, c);
             float4 v = *(const float4*)src;
             if (DIRECT) v = make_float4(sc * v.x, sc * v.y, sc * v.z, sc * v.w);
-            red_add4(dst + c, v);
+            red_add4_sys(dst + c, v);
             *(float4*)src = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         if (lane == 0) {
             float* sb = a.scratch_bias[e] + s;
             if (DIRECT) {
-                red_add1((float*)(e == 0 ? ldg_ptr(&pt->user_bias) : ldg_ptr(&pt->item_bias)) + lrow, sc * *sb);
+                red_add1_sys((float*)(e == 0 ? ldg_ptr(&pt->user_bias) : ldg_ptr(&pt->item_bias)) + lrow, sc * *sb);
             } else {
-                red_add1((e == 0 ? ldg_ptr(&pt->g_user_bias) : ldg_ptr(&pt->g_item_bias)) + lrow, *sb);
+                red_add1_sys((e == 0 ? ldg_ptr(&pt->g_user_bias) : ldg_ptr(&pt->g_item_bias)) + lrow, *sb);
                 red_or_u32((e == 0 ? ldg_ptr(&pt->user_bits) : ldg_ptr(&pt->item_bits)) + (lrow >> 5), 1u << (lrow & 31));
             }
             *sb = 0.f;

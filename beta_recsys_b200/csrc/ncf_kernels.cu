@@ -72,7 +72,7 @@ __device__ __forceinline__ bool fetch_ids(const NcfArgs& a, long long s, int lan
     u = a.users[s];
     i = a.items[s];
     if ((unsigned long long)u >= (unsigned long long)a.n_users || (unsigned long long)i >= (unsigned long long)a.n_items) {
-        if (lane == 0 && !a.train) atomicOr(&a.ws->err_flag, 1u);
+        if (lane == 0 && !a.train) atomicOr(&a.ws->predict_err, 1u);
         u = i = 0;
         return false;
     }

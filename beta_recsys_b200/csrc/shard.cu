@@ -10,9 +10,15 @@
 // NCCL all-to-all routing of triples to the user-row owner.
 #include <string.h>
 
+#include <stdio.h>
+
 #include "common.cuh"
 
 namespace {
+
+// ~20 s at 2 GHz: far beyond any legitimate skew between ranks (a step is ~100 us), short enough that a hung
+// job ends inside the caller's own timeout
+constexpr long long kBarrierTimeoutCycles = 40ll * 1000 * 1000 * 1000;
 
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
@@ -49,7 +55,15 @@ __global__ void __launch_bounds__(32) peer_barrier_kernel(const BarrierArgs a) {
     __threadfence_system();  // everything this GPU wrote before (incl. earlier kernels' peer REDs) first
     if (p < a.world) st_release_sys(a.flags[p] + a.rank, a.epoch);
     if (p < a.world) {
+        // bounded wait: a peer that left the step sequence (error return, exception) never posts its flag;
+        // trap instead of spinning forever with a resident kernel -- the launch fails with a sticky error on
+        // this rank, which the host reports, and the process group tears down
+        const long long t0 = clock64();
         while (ld_acquire_sys(a.flags[a.rank] + p) < a.epoch) {
+            if (clock64() - t0 > kBarrierTimeoutCycles) {
+                printf("brs: peer barrier timed out on rank %d waiting for rank %d (epoch %lld)\n", a.rank, p, (long long)a.epoch);
+                __trap();
+            }
         }
     }
     __syncwarp();

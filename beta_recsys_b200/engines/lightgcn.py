@@ -162,9 +162,10 @@ class LightGCNEngine(ModelEngine):
         lib = _lib.load()
         users, items = as_index(users, self.device), as_index(items, self.device)
         self.propagate(None)
-        out = torch.empty(users.numel(), dtype=torch.float32, device=self.device)
+        out = torch.full((users.numel(),), float("nan"), dtype=torch.float32, device=self.device)
         _lib.check(lib.brs_lightgcn_scores(self._cmodel, _lib.ptr(users), _lib.ptr(items), users.numel(), _lib.ptr(out),
                                            self._stream()), "brs_lightgcn_scores")
+        self._check_predict()
         return out
 
     def train_single_batch(self, batch_data, keep_mask=None):

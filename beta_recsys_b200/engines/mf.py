@@ -139,6 +139,7 @@ class MFEngine(ModelEngine):
         out = torch.empty(users.numel(), dtype=torch.float32, device=self.device)
         _lib.check(lib.brs_mf_predict(self._cmodel, _lib.ptr(users), _lib.ptr(items), users.numel(), _lib.ptr(out),
                                       self._stream()), "brs_mf_predict")
+        self._check_predict()
         return out
 
     def _launch_step(self, batch_data, out):

@@ -214,9 +214,10 @@ class _NcfEngine(ModelEngine):
         users, items = as_index(users, self.device), as_index(items, self.device)
         if users.numel() != items.numel():
             raise ValueError("users and items must have the same length")
-        out = torch.empty(users.numel(), dtype=torch.float32, device=self.device)
+        out = torch.full((users.numel(),), float("nan"), dtype=torch.float32, device=self.device)
         _lib.check(lib.brs_ncf_predict(self._cmodel, _lib.ptr(users), _lib.ptr(items), users.numel(), _lib.ptr(out),
                                        self._stream()), "brs_ncf_predict")
+        self._check_predict()
         return out
 
     def train_single_batch(self, users, items, ratings):

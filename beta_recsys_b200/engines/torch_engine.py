@@ -110,6 +110,16 @@ class ModelEngine(object):
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream
 
+    def _check_predict(self):
+        """The no_grad scoring kernels raise their OWN error word (brs_step_ws.predict_err, byte 44 of the
+        workspace) for an out-of-range id -- never the training step's -- and publish NaN for that sample.
+        Reading it costs one 4-byte D2H; predict's callers move the scores to the host right after
+        (core/eval_engine.py:258-273).  The reference raises IndexError inside nn.Embedding."""
+        word = self._ws[44:48].view(torch.int32)
+        if int(word.item()):
+            word.zero_()
+            raise IndexError("index out of range in self")
+
     def save_checkpoint(self, model_dir):
         """torch_engine.py:70-73 -- same state_dict keys/shapes as the reference module."""
         assert hasattr(self, "model"), "Please specify the exact model !"

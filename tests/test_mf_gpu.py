@@ -352,6 +352,33 @@ def test_mf_out_of_range_index_raises_and_engine_recovers():
     eng.train_single_batch(cuda_batch(u, i, j))  # still usable afterwards
 
 
+def test_mf_predict_out_of_range_raises_and_does_not_poison_training(step_impl):
+    """predict has its own error word -- an invalid id raises IndexError from predict itself
+    (the reference raises inside nn.Embedding) and the next, valid training step is unaffected."""
+    rng = np.random.default_rng(2)
+    nu, ni, d, bsz = 30, 20, 16, 64
+    p = random_state(rng, nu, ni, d)
+    eng = make_engine(nu, ni, d, bsz, "sgd", 0.05, "bpr", state=p)
+    with pytest.raises(IndexError):
+        eng.model.predict(np.array([1, nu]), np.array([1, 1]))
+    with pytest.raises(IndexError):
+        eng.model.predict(np.array([1, 2]), np.array([-1, 1]))
+    assert np.isfinite(eng.model.predict(np.array([1, 2]), np.array([3, 4])).cpu().numpy()).all()
+    u, i, j = rng.integers(0, nu, bsz), rng.integers(0, ni, bsz), rng.integers(0, ni, bsz)
+    before = snap(eng)
+    eng.train_single_batch(cuda_batch(u, i, j))  # no spurious IndexError from the earlier predict
+    if step_impl == "rows":  # the row-owner step voids a step with a bad index: parameters stay untouched
+        mid = snap(eng)
+        bad = u.copy()
+        bad[7] = -3
+        with pytest.raises(IndexError):
+            eng.train_single_batch(cuda_batch(bad, i, j))
+        after = snap(eng)
+        for k in mid:
+            assert np.array_equal(mid[k], after[k]), k
+        assert any(not np.array_equal(before[k], mid[k]) for k in mid)
+
+
 def test_mf_unsupported_loss_and_dim():
     from beta_recsys_b200 import BrsError
 
