@@ -1,8 +1,13 @@
 #!/usr/bin/env python
 """bench.py -- BPR interactions/sec of the MF training hot path on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 2|3|4|5]
                     [--optimizer sgd|adam] [--adam-mode dense|touched] [--dim D] [--batch B]
+
+--config 2 (default, the driver's line) is described below; 3 = NeuMF 10M x 1M, 4 = LightGCN 1M x 100k,
+5 = gather / scatter microbench over a 100M-row table -- one GPU each, see bench_configs.py.
+With --gpus N > 1 config 2 runs on the 10M x 1M row-sharded tables BASELINE's scaling target names and
+carries a `parity` block (small seeded global batch against the oracle, before the timed region).
 
 Workload (BASELINE.json configs[1], SURVEY.md section 8d "cfg 2"): MF-BPR, 1M users x 100k
 items, dim 128, batch 65536, SGD lr 0.05; 256 pre-built batches of synthetic
@@ -45,8 +50,15 @@ def parse():
     ap.add_argument("--adam-mode", default="dense", choices=["dense", "touched"])
     ap.add_argument("--dim", type=int, default=128)
     ap.add_argument("--batch", type=int, default=65536)
-    ap.add_argument("--users", type=int, default=N_USERS)
-    ap.add_argument("--items", type=int, default=N_ITEMS)
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5], help="BASELINE.json configs[] index + 1")
+    ap.add_argument("--users", type=int, default=0, help="0 = the configuration's own size")
+    ap.add_argument("--items", type=int, default=0)
+    ap.add_argument("--edges", type=int, default=20_000_000, help="config 4: interactions of the synthetic graph")
+    ap.add_argument("--rows", type=int, default=100_000_000, help="config 5: table rows")
+    ap.add_argument("--dropout-rng", default="cuda", choices=["cuda", "cpu"],
+                    help="config 4: 'cpu' draws the edge mask with the reference's own torch.rand(nnz) on the host "
+                         "(bit-identical mask, ~10x slower step); 'cuda' draws it on the device")
+    ap.add_argument("--no-parity", action="store_true", help="multi-GPU: skip the parity block")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--profile", action="store_true",
@@ -60,6 +72,14 @@ def parse():
                          "benchmark line is quoted at the default 1.05)")
     a = ap.parse_args()
     globals()["ZIPF_A"] = a.zipf_a
+    if a.config == 3:
+        a.users, a.items = a.users or 10_000_000, a.items or 1_000_000
+        if a.adam_mode == "dense" and "--adam-mode" not in sys.argv:
+            a.adam_mode = "touched"  # the reference-exact dense sweep streams 42 GB per step; named in the line
+    elif a.gpus > 1:  # the scaling target is stated on 10M x 1M row-sharded tables
+        a.users, a.items = a.users or 10_000_000, a.items or 1_000_000
+    else:
+        a.users, a.items = a.users or N_USERS, a.items or N_ITEMS
     return a
 
 
@@ -102,14 +122,17 @@ def make_batches(n_users, n_items, batch, n_batches, seed, device):
 
 def config_dict(a, world):
     return {
-        "workload": "configs[1]: MF BPR %dM users x %dk items, dim=%d, batch=%d, 1xB200 per rank"
-                    % (a.users // 1_000_000, a.items // 1000, a.dim, a.batch),
+        "workload": ("configs[1]: MF BPR %dM users x %dk items, dim=%d, batch=%d, 1xB200"
+                     % (a.users // 1_000_000, a.items // 1000, a.dim, a.batch)) if world == 1 else
+                    ("configs[1] at the scaling target's table size: MF BPR %dM users x %dM items row-sharded over %d B200, "
+                     "dim=%d, batch=%d per rank" % (a.users // 1_000_000, a.items // 1_000_000, world, a.dim, a.batch)),
         "n_users": a.users, "n_items": a.items, "dim": a.dim, "batch_per_gpu": a.batch,
         "global_batch": a.batch * world, "optimizer": a.optimizer,
         "optimizer_mode": ("exact (SGD touches only batch rows)" if a.optimizer == "sgd" else a.adam_mode),
         "lr": 0.05, "index_distribution": "user,pos ~ Zipf(%g) on permuted ids; neg ~ Uniform" % ZIPF_A,
         "prebuilt_batches": N_PREBUILT,
-        "l2_policy": "inputs larger than L2: 563 MB of tables, %d distinct batches cycled" % N_PREBUILT,
+        "l2_policy": "inputs larger than L2: %.0f MB of tables per rank, %d distinct batches cycled"
+                     % ((a.users + a.items) * (a.dim + 1) * 4 / 1e6 / world, N_PREBUILT),
         "parallelism": "dp%d" % world if world > 1 else "single",
     }
 
@@ -203,11 +226,32 @@ def cpu_baseline(a, n_timed=0, budget_s=20.0):
         port.train_single_batch(batches[k % nb])
         times.append(time.time() - t0)
     med = float(np.median(times))
+    # the same step INCLUDING the reference's DataLoader -- one batch drawn the way
+    # DataLoader(PairwiseNegativeDataset, shuffle=True) draws it: per-sample __getitem__ on three tensors, then
+    # default_collate (beta_rec/data/data_loaders.py:30-53, base_data.py:253).  One batch is timed (it takes ~1 s).
+    from torch.utils.data import DataLoader, Dataset
+
+    class _Pairwise(Dataset):  # data_loaders.py:30-53
+        def __init__(self, u, p, n):
+            self.user_tensor, self.pos_item_tensor, self.neg_item_tensor = u, p, n
+
+        def __getitem__(self, index):
+            return self.user_tensor[index], self.pos_item_tensor[index], self.neg_item_tensor[index]
+
+        def __len__(self):
+            return self.user_tensor.size(0)
+
+    ds = _Pairwise(torch.cat([x[0] for x in batches]), torch.cat([x[1] for x in batches]), torch.cat([x[2] for x in batches]))
+    it = iter(DataLoader(ds, batch_size=a.batch, shuffle=True))
+    t0 = time.time()
+    next(it)
+    loader_s = time.time() - t0
     return {"value": a.batch / med, "unit": "interactions/s", "cores": cores, "kind": "port",
             "sample": "%d timed + 2 warm-up train_single_batch calls of the reference's torch-CPU step "
                       "(oracle/torch_port.py: dense autograd + torch.optim.%s), same shapes as the GPU run, "
-                      "median %.1f ms/step; DataLoader excluded" % (n_timed, a.optimizer.upper(), med * 1e3),
-            "ms_per_step": med * 1e3}
+                      "median %.1f ms/step; DataLoader excluded (with the reference's DataLoader: + %.0f ms per batch, "
+                      "see value_with_loader)" % (n_timed, a.optimizer.upper(), med * 1e3, loader_s * 1e3),
+            "ms_per_step": med * 1e3, "loader_ms_per_batch": loader_s * 1e3, "value_with_loader": a.batch / (med + loader_s)}
 
 
 def cpu_model_name():
@@ -227,12 +271,27 @@ def run_reference(a):
     rank, world, _ = dist_env()
     if rank != 0:
         return
+    if a.config != 2:
+        import bench_configs as bc
+
+        fn, metric = {3: (bc.cpu_neumf, "BCE interactions/sec (NeuMF)"),
+                      4: (bc.cpu_lightgcn, "BPR interactions/sec (LightGCN, whole-graph propagate per batch)"),
+                      5: (bc.cpu_gather, "embedding gather HBM GB/s (D=128)")}[a.config]
+        cb = fn(a)
+        print(json.dumps({"impl": "reference", "metric": metric, "value": cb["value"], "unit": cb["unit"], "n_gpus": a.gpus,
+                          "steps": a.steps, "warmup": a.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                          "dtype": "f32", "data": "synthetic", "config": {"workload": "BASELINE configs[%d], CPU sample" % (a.config - 1)},
+                          "cpu_baseline": cb, "cpu_model": cpu_model_name(),
+                          "e2e": {"value": cb["value"], "unit": cb["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                          "gpu_launches": 0}))
+        return
     cb = cpu_baseline(a, n_timed=max(1, min(a.steps, 40)) if a.cpu_steps == 0 else a.cpu_steps)
     line = {
         "impl": "reference", "metric": "BPR interactions/sec", "value": cb["value"], "unit": "interactions/s",
         "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": cb["ms_per_step"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": config_dict(a, 1), "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "config": config_dict(a, 1),
+        "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "loader_ms_per_batch", "value_with_loader")},
         "cpu_model": cpu_model_name(),
         "e2e": {"value": cb["value"], "unit": "interactions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -256,6 +315,13 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def measured_tflops():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"])
+    except Exception:
+        return 1590.0
+
+
 def ncu_traffic():
     """dram bytes per fwd_bwd launch from the committed ncu --set full capture, if any."""
     p = os.path.join(ROOT, "profiles", "roofline_latest.json")
@@ -265,6 +331,82 @@ def ncu_traffic():
         return None
 
 
+def sharded_parity(a, rank, world, local, dev):
+    """Multi-GPU parity, run before the timed region on every `--gpus N > 1` launch: a small seeded model
+    (5003 x 1999, dim = the bench's), each rank fed its own batch, against the oracle run on the concatenated
+    global batch -- 3 SGD steps and 1 dense-Adam step in BOTH shard modes (per-sample peer gathers / pull +
+    staging).  The oracle is the checker here, nothing of it is timed or shipped (oracle/__init__.py)."""
+    import torch.distributed as dist
+
+    from beta_recsys_b200 import _lib
+    from beta_recsys_b200.sharded import ShardedMFEngine
+    from oracle import cf_oracle as O  # checker only
+
+    nu, ni, d, bsz, lr = 5003, 1999, a.dim, 1024, 0.05
+    out = {"max_rel_dw": 0.0, "max_rel_loss": 0.0, "global_bias_bit_identical": True, "cases": []}
+
+    def zipf(rng, n, size):
+        p = np.arange(1, n + 1, dtype=np.float64) ** (-1.05)
+        p /= p.sum()
+        return rng.permutation(n)[rng.choice(n, size=size, p=p)].astype(np.int64)
+
+    for mode in (1, 2):
+        for optimizer, steps in (("sgd", 3), ("adam", 1)):
+            _lib.check(_lib.load().brs_debug_set_shard_mode(mode))
+            rng = np.random.default_rng(7)  # same on every rank: the global model and all ranks' batches
+            p = {"global_bias": np.array([0.03], dtype=np.float32),
+                 "user_emb.weight": rng.normal(0, 0.1, (nu, d)).astype(np.float32),
+                 "item_emb.weight": rng.normal(0, 0.1, (ni, d)).astype(np.float32),
+                 "user_bias.weight": rng.normal(0, 0.1, (nu, 1)).astype(np.float32),
+                 "item_bias.weight": rng.normal(0, 0.1, (ni, 1)).astype(np.float32)}
+            cfg = {"model": dict(device_str="cuda:%d" % local, n_users=nu, n_items=ni, emb_dim=d, batch_size=bsz,
+                                 optimizer=optimizer, lr=lr, loss="bpr", adam_mode="dense")}
+            eng = ShardedMFEngine(cfg, route="none", state=p)
+            st = O.new_opt_state(p, optimizer)
+            worst_dw, worst_loss = 0.0, 0.0
+            for t in range(steps):
+                batches = [(zipf(rng, nu, bsz), zipf(rng, ni, bsz), rng.integers(0, ni, bsz)) for _ in range(world)]
+                before = {k: v.copy() for k, v in p.items()}
+                loss, reg = eng.train_single_batch(tuple(torch.from_numpy(x).to(dev) for x in batches[rank]))
+                g = tuple(np.concatenate([b[c] for b in batches]) for c in range(3))
+                ol, orr = O.mf_train_single_batch(p, st, g, "bpr", optimizer, lr, 0.0)
+                worst_loss = max(worst_loss, abs(loss - ol) / max(1.0, abs(ol)), abs(reg - orr) / max(1.0, abs(orr)))
+                got = eng.gather_state()
+                for k in p:  # this step's UPDATE against the oracle's, relative to max|dw| (+ 2 ulp of the fp32 parameter)
+                    if k == "global_bias":
+                        continue  # sums 2B opposite-sign terms: covered by the bit-identity check below and the loss
+                    dw = p[k].astype(np.float64) - before[k]
+                    dg = got[k].astype(np.float64) - before[k]
+                    ulp = 2.0 * np.spacing(np.maximum(np.abs(p[k]), np.abs(before[k])).astype(np.float32)).astype(np.float64)
+                    err = np.maximum(np.abs(dg - dw) - ulp, 0.0).max() / max(np.abs(dw).max(), 1e-30)
+                    if optimizer == "adam":  # lr*m/(sqrt(v)+eps) is ill-conditioned in fp32 where g ~ eps: bound by lr
+                        err = np.abs(dg - dw).max() / lr
+                    worst_dw = max(worst_dw, float(err))
+                for k in p:  # the oracle continues from the GPU's own state: per-step parity, no trajectory drift
+                    p[k] = got[k].copy()
+            gb = [torch.empty(1, device=dev) for _ in range(world)]
+            dist.all_gather(gb, eng.global_bias)
+            same = all(torch.equal(gb[0], x) for x in gb)
+            eng.close()
+            out["cases"].append({"shard_mode": {1: "direct", 2: "staged"}[mode], "optimizer": optimizer, "steps": steps,
+                                 "max_rel_dw": worst_dw, "max_rel_loss": worst_loss})
+            out["max_rel_dw"] = max(out["max_rel_dw"], worst_dw if optimizer == "sgd" else 0.0)
+            out["max_rel_loss"] = max(out["max_rel_loss"], worst_loss)
+            out["global_bias_bit_identical"] = out["global_bias_bit_identical"] and same
+    _lib.check(_lib.load().brs_debug_set_shard_mode(0))
+    adam_err = max(c["max_rel_dw"] for c in out["cases"] if c["optimizer"] == "adam")
+    out["adam_max_abs_dw_over_lr"] = adam_err
+    out["pass"] = bool(out["max_rel_dw"] <= 1e-4 and out["max_rel_loss"] <= 1e-5 and adam_err <= 2e-3 and
+                       out["global_bias_bit_identical"])
+    out["what"] = ("5003 x 1999 x dim %d, batch %d per rank, %d ranks: sharded engines (each rank its own batch) vs the numpy "
+                   "oracle on the concatenated global batch; SGD updates relative to max|dw| (tolerance 1e-4 + 2 ulp), losses "
+                   "1e-5, dense-Adam first step |dw| error / lr" % (d, bsz, world))
+    flag = torch.tensor([1.0 if out["pass"] else 0.0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    out["pass_all_ranks"] = bool(flag.item() == 1.0)
+    return out
+
+
 def run_sharded(a, rank, world, local, dev):
     """N > 1: tables row-sharded over the ranks (owner = row mod N), per-rank batch fixed (weak scaling).
     Rows travel over NVLink peer memory inside the fused kernel; two flag barriers per step."""
@@ -272,6 +414,7 @@ def run_sharded(a, rank, world, local, dev):
 
     from beta_recsys_b200.sharded import ShardedMFEngine
 
+    parity = None if a.no_parity or a.profile else sharded_parity(a, rank, world, local, dev)
     cfg = {"model": dict(device_str="cuda:%d" % local, n_users=a.users, n_items=a.items, emb_dim=a.dim,
                          batch_size=a.batch, optimizer=a.optimizer, lr=0.05, loss="bpr", adam_mode=a.adam_mode)}
     eng = ShardedMFEngine(cfg, route=a.route)
@@ -398,7 +541,7 @@ def run_sharded(a, rank, world, local, dev):
             "clocks": clocks, "e2e": e2e,
             # pre-pass, [pull,] fused fwd/bwd, barrier, push, count reset, apply/record, barrier
             "gpu_launches": (8 if os.environ.get("BRS_SHARD_MODE", "2" if world >= 8 else "1") == "2" else 7) * a.steps,
-            "final_loss": final_loss, "wall_s_timed_region": t_wall1 - t_wall0,
+            "final_loss": final_loss, "wall_s_timed_region": t_wall1 - t_wall0, "parity": parity,
         }
         print(json.dumps(line))
     dist.destroy_process_group()
@@ -409,6 +552,8 @@ def run_ours(a):
     from beta_recsys_b200.engines import MFEngine
 
     rank, world, local = dist_env()
+    if a.config != 2 and a.gpus != 1:
+        raise SystemExit("--config %d is a single-GPU line (see bench_configs.py); run it with --gpus 1" % a.config)
     if world != a.gpus:
         if a.gpus == 1:
             world, rank, local = 1, 0, 0
@@ -422,6 +567,22 @@ def run_ours(a):
         dist.init_process_group("nccl", device_id=dev)
         return run_sharded(a, rank, world, local, dev)
     lib = _lib.load()
+    if a.config != 2:
+        import bench_configs as bc
+
+        sampler = ClockSampler(local)
+        sampler.start()
+        peak, peak_src = measured_peak()
+        fn, cpu_fn = {3: (bc.run_neumf, bc.cpu_neumf), 4: (bc.run_lightgcn, bc.cpu_lightgcn),
+                      5: (bc.run_microbench, bc.cpu_gather)}[a.config]
+        line = fn(a, dev, sampler, (peak, peak_src, measured_tflops()))
+        sampler.stop()
+        line.pop("cpu_baseline_fn", None)
+        if not a.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_fn(a)
+            line["cpu_model"] = cpu_model_name()
+        print(json.dumps(line))
+        return
 
     cfg = {"model": dict(device_str="cuda:%d" % local, n_users=a.users, n_items=a.items, emb_dim=a.dim,
                          batch_size=a.batch, optimizer=a.optimizer, lr=0.05, loss="bpr", adam_mode=a.adam_mode),
@@ -436,6 +597,7 @@ def run_ours(a):
     stream = torch.cuda.current_stream(dev)
 
     overlap = a.optimizer == "sgd" or a.adam_mode == "touched"
+    rows_impl = eng._step_impl == "rows"
     launch_count = [0]
 
     def run_steps(k, first_batch):
@@ -451,7 +613,10 @@ def run_ours(a):
                                                 _lib.ptr(out), stream.cuda_stream), "train_batches")
             # touched-rows optimizers: slot pre-pass of batch 0, then per batch the fused kernel and ONE launch
             # that applies batch b and claims the slots of batch b+1; dense Adam/RMSprop: 5 launches per batch
-            launch_count[0] += (1 + 2 * nb) if overlap else 5 * nb
+            if rows_impl:  # per batch: plan (claim, segment, fill) + users + items kernels (+ the dense sweep)
+                launch_count[0] += (5 if overlap else 6) * nb
+            else:
+                launch_count[0] += (1 + 2 * nb) if overlap else 5 * nb
             done += nb
             b = (b + nb) % N_PREBUILT
         return out
@@ -490,24 +655,65 @@ def run_ours(a):
     t_load1 = time.time()
     clocks = sampler.summary(t_load0, t_load1)
 
-    # ---- per-kernel durations: instrumented replay of the same steps ----
-    n_inst = min(a.steps, 200) if not a.profile else 3
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(n_inst)]
+    # ---- per-kernel durations on a second engine (the timed one keeps its state for the e2e leg) ----
+    with redirect_stdout(io.StringIO()):
+        eng_i = MFEngine(cfg)
+    kernel_ms = {}
     out1 = torch.empty(4, dtype=torch.float32, device=dev)
-    for k in range(n_inst):
-        off = ((a.warmup + k) % N_PREBUILT) * a.batch
-        bu, bp, bn = _lib.ptr(users[off:]), _lib.ptr(pos[off:]), _lib.ptr(neg[off:])
-        ev[k][0].record(stream)
-        _lib.check(lib.brs_mf_bpr_prepare(eng._cmodel, bu, bp, bn, a.batch, stream.cuda_stream))
-        ev[k][1].record(stream)
-        _lib.check(lib.brs_mf_bpr_fwd_bwd_prepared(eng._cmodel, bu, bp, bn, a.batch, 0.0, stream.cuda_stream))
-        ev[k][2].record(stream)
-        _lib.check(lib.brs_mf_apply(eng._cmodel, eng.optimizer.desc, a.batch, _lib.ptr(out1), stream.cuda_stream))
-        ev[k][3].record(stream)
-    torch.cuda.synchronize(dev)
-    t_prep = float(np.median([e[0].elapsed_time(e[1]) for e in ev]))  # ms
-    t_fwd = float(np.median([e[1].elapsed_time(e[2]) for e in ev]))
-    t_apply = float(np.median([e[2].elapsed_time(e[3]) for e in ev]))
+    if rows_impl:
+        # GPU-bound times: each launch sequence is captured into a CUDA graph and replayed, which keeps the host's
+        # launch cost (Python, ctypes, driver) out of the CUDA-event interval
+        def graph_ms(fn, inner, reps=20 if not a.profile else 2):
+            side = torch.cuda.Stream(device=dev)
+            with torch.cuda.stream(side):
+                fn(side.cuda_stream)
+            torch.cuda.synchronize(dev)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):
+                for _ in range(inner):
+                    fn(torch.cuda.current_stream(dev).cuda_stream)
+            g.replay()
+            torch.cuda.synchronize(dev)
+            q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            q0.record()
+            for _ in range(reps):
+                g.replay()
+            q1.record()
+            torch.cuda.synchronize(dev)
+            return q0.elapsed_time(q1) / (reps * inner)
+
+        bu, bp, bn = _lib.ptr(users), _lib.ptr(pos), _lib.ptr(neg)
+        _lib.check(lib.brs_mf_plan_build(eng_i._cmodel, 0, 0, bu, bp, bn, a.batch, stream.cuda_stream))
+        torch.cuda.synchronize(dev)
+        for which, name in ((1, "mf_user_rows_kernel"), (2, "mf_item_rows_kernel")):
+            lib.brs_debug_set_mf_rows_only(which)
+            kernel_ms[name] = graph_ms(lambda st: _lib.check(lib.brs_mf_step_planned(
+                eng_i._cmodel, 0, eng_i.optimizer.desc, 0, a.batch, 0.0, _lib.ptr(out1), st)), 4)
+        lib.brs_debug_set_mf_rows_only(0)
+        kernel_ms["plan (mf_plan_claim + segment + fill, side stream)"] = graph_ms(
+            lambda st: _lib.check(lib.brs_mf_plan_build(eng_i._cmodel, 0, 0, bu, bp, bn, a.batch, st)), 1)
+        t_prep = kernel_ms["plan (mf_plan_claim + segment + fill, side stream)"]
+        t_fwd, t_apply = kernel_ms["mf_user_rows_kernel"], kernel_ms["mf_item_rows_kernel"]
+    else:
+        n_inst = min(a.steps, 200) if not a.profile else 3
+        ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(n_inst)]
+        for k in range(n_inst):
+            off = ((a.warmup + k) % N_PREBUILT) * a.batch
+            bu, bp, bn = _lib.ptr(users[off:]), _lib.ptr(pos[off:]), _lib.ptr(neg[off:])
+            ev[k][0].record(stream)
+            _lib.check(lib.brs_mf_bpr_prepare(eng_i._cmodel, bu, bp, bn, a.batch, stream.cuda_stream))
+            ev[k][1].record(stream)
+            _lib.check(lib.brs_mf_bpr_fwd_bwd_prepared(eng_i._cmodel, bu, bp, bn, a.batch, 0.0, stream.cuda_stream))
+            ev[k][2].record(stream)
+            _lib.check(lib.brs_mf_apply(eng_i._cmodel, eng_i.optimizer.desc, a.batch, _lib.ptr(out1), stream.cuda_stream))
+            ev[k][3].record(stream)
+        torch.cuda.synchronize(dev)
+        t_prep = float(np.median([e[0].elapsed_time(e[1]) for e in ev]))  # ms
+        t_fwd = float(np.median([e[1].elapsed_time(e[2]) for e in ev]))
+        t_apply = float(np.median([e[2].elapsed_time(e[3]) for e in ev]))
+        kernel_ms = {"assign_slots_kernel (pre-pass)": t_prep, "mf_fwd_bwd_kernel": t_fwd, "rows_apply_kernel": t_apply}
+    del eng_i
+    torch.cuda.empty_cache()
 
     # ---- end to end through the public API with HOST index buffers ----
     e2e = None
@@ -577,17 +783,21 @@ def run_ours(a):
     value = a.steps * a.batch * world / (ms * 1e-3)
     peak, peak_src = measured_peak()
     alg = algorithmic_bytes_per_interaction(a.dim, a.optimizer) * a.batch
-    achieved = alg / (t_fwd * 1e-3) / 1e9
-    step_achieved = alg / ((t_prep + t_fwd + t_apply) * 1e-3) / 1e9
+    step_ms = ms / a.steps
+    achieved = alg / (step_ms * 1e-3) / 1e9  # the WHOLE step: every launch the update needs is inside this time
+    per_kernel = {k: {"ms": v, "alg_GBps_if_alone": alg / (v * 1e-3) / 1e9} for k, v in kernel_ms.items()}
     roofline = {
-        "bound": "hbm", "kernel": "mf_fwd_bwd_kernel (gather 3 rows -> dot/BPR -> red.add 3 gradient rows)",
+        "bound": "hbm",
+        "kernel": ("MF step = mf_user_rows_kernel + mf_item_rows_kernel (row-owner gather -> dot/BPR -> in-register gradient -> "
+                   "in-place row update), index plan of the next batch on a side stream") if rows_impl else
+                  "MF step = assign_slots + mf_fwd_bwd_kernel (gather -> dot/BPR -> red.add) + rows_apply_kernel",
         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
-        "traffic": ncu_traffic(),
-        "algorithmic_bytes_per_launch": alg, "kernel_ms": t_fwd, "apply_kernel_ms": t_apply,
-        "prepass_kernel_ms": t_prep,
-        "step_achieved": step_achieved, "step_frac": step_achieved / peak,
-        "note": "achieved = (24*D+48 B per interaction x batch) / median CUDA-event duration of the fwd_bwd launch in an "
-                "instrumented replay of the timed steps; step_* divides the same bytes by slot pre-pass + fwd_bwd + rows_apply",
+        "traffic": ncu_traffic(), "algorithmic_bytes_per_launch": alg, "step_ms": step_ms, "kernels": per_kernel,
+        "serial_kernel_ms": t_prep + t_fwd + t_apply,
+        "note": "achieved = (24*D+48 B per interaction x batch) / CUDA-event time of one WHOLE step in the timed region "
+                "(all kernels of the step, not the fused kernel alone); `kernels` are per-launch times of the same step "
+                + ("from CUDA-graph replays on a fixed batch (GPU-bound, warm L2)" if rows_impl else
+                   "from an instrumented replay") + "; traffic = dram bytes of the step's kernels from the committed ncu capture",
     }
     line = {
         "metric": "BPR interactions/sec", "value": value, "unit": "interactions/s", "n_gpus": world,
@@ -598,7 +808,8 @@ def run_ours(a):
     }
     if world == 1 and not a.no_cpu_baseline:
         cb = cpu_baseline(a, n_timed=a.cpu_steps)
-        line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "loader_ms_per_batch",
+                                                   "value_with_loader")}
         line["cpu_model"] = cpu_model_name()
     print(json.dumps(line))
     if world > 1:
