@@ -394,6 +394,89 @@ class ShardedMFEngine(object):
             out[key] = unshard([p.cpu().numpy() for p in parts], n)
         return out
 
+    _TABLES = (("user_emb", "user_emb.weight", "n_users"), ("item_emb", "item_emb.weight", "n_items"),
+               ("user_bias", "user_bias.weight", "n_users"), ("item_bias", "item_bias.weight", "n_items"))
+
+    def _gather_full(self, local, n_rows):
+        parts = [torch.empty_like(local) for _ in range(self.world)]
+        dist.all_gather(parts, local.contiguous(), group=self.group)
+        return unshard([p.cpu().numpy() for p in parts], n_rows)
+
+    def gather_optimizer_state(self):
+        """Optimizer state in the layout of torch.optim's state_dict()["state"] for the reference module's
+        parameter order (global_bias, user_emb, item_emb, user_bias, item_bias -- models/mf.py:17-30):
+        {index: {"step", "exp_avg", "exp_avg_sq"}} for Adam, {"step", "square_avg"} for RMSprop, {} for SGD.
+        Identical on every rank."""
+        step = int(self.arena.tensor("ws")[24:32].view(torch.int64).item())  # brs_step_ws.step
+        names = {"m": "exp_avg", "v": "exp_avg_sq"} if self.opt_kind == "adam" else {"v": "square_avg"}
+        out = {}
+        order = [("global_bias", None, None)] + [(n, k, r) for n, k, r in self._TABLES]
+        for idx, (name, _, rows_attr) in enumerate(order):
+            st = self.state[name]
+            if not st:
+                continue
+            ent = {"step": torch.tensor(float(step))}
+            for kind, tname in names.items():
+                if kind not in st:
+                    continue
+                full = st[kind].cpu().numpy().copy() if rows_attr is None else self._gather_full(st[kind], getattr(self, rows_attr))
+                ent[tname] = torch.from_numpy(full)
+            out[idx] = ent
+        return out
+
+    def save_checkpoint(self, model_dir):
+        """ModelEngine.save_checkpoint (beta_rec/models/torch_engine.py:70-73) for the sharded tables: the shards
+        are gathered into the reference module's ``state_dict`` (same keys, shapes, dtypes) and rank 0 writes it
+        with ``torch.save`` -- the file loads into the reference's own ``MF`` module or into the single-GPU
+        ``MFEngine``.  The optimizer state goes to ``model_dir + ".optim"`` (the reference does not save it;
+        resuming Adam without it restarts the moments).  Collective: every rank must call it."""
+        state = self.gather_state()
+        opt_state = self.gather_optimizer_state()
+        if self.rank == 0:
+            torch.save({k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in state.items()}, model_dir)
+            torch.save({"optimizer": self.opt_kind, "lr": self.lr, "state": opt_state}, model_dir + ".optim")
+        dist.barrier(group=self.group)
+
+    def resume_checkpoint(self, model_dir, load_optimizer=True):
+        """ModelEngine.resume_checkpoint (torch_engine.py:76-90): every rank reads the reference-layout file and
+        keeps its own rows (owner = row mod world); the replicated global bias is copied whole.  Works for a
+        checkpoint written by the reference, by MFEngine or by any world size of this engine."""
+        print("loading model from:", model_dir)
+        sd = torch.load(model_dir, map_location="cpu")
+        want = {"global_bias"} | {k for _, k, _ in self._TABLES}
+        if set(sd) != want:
+            raise RuntimeError("checkpoint keys do not match the model: %s" % sorted(set(sd) ^ want))
+        t = self.arena.tensor
+        with torch.no_grad():
+            for name, key, rows_attr in self._TABLES:
+                full = sd[key].numpy()
+                if full.shape[0] != getattr(self, rows_attr) or full.shape[1:] != tuple(t(name).shape[1:]):
+                    raise RuntimeError("size mismatch for %s: checkpoint %s" % (key, tuple(full.shape)))
+                t(name).copy_(torch.from_numpy(shard_of(full.astype(np.float32, copy=False), self.world, self.rank)))
+            self.global_bias.copy_(sd["global_bias"].to(torch.float32).view(-1))
+            opt_path = model_dir + ".optim"
+            import os
+
+            if load_optimizer and self.opt_kind != "sgd" and os.path.exists(opt_path):
+                od = torch.load(opt_path, map_location="cpu")
+                if od["optimizer"] != self.opt_kind:
+                    raise RuntimeError("optimizer state is for %s, the engine runs %s" % (od["optimizer"], self.opt_kind))
+                names = {"m": "exp_avg", "v": "exp_avg_sq"} if self.opt_kind == "adam" else {"v": "square_avg"}
+                order = [("global_bias", None)] + [(n, r) for n, _, r in self._TABLES]
+                step = 0
+                for idx, (name, rows_attr) in enumerate(order):
+                    ent = od["state"].get(idx)
+                    if ent is None:
+                        continue
+                    step = int(ent["step"])
+                    for kind, tname in names.items():
+                        full = ent[tname].numpy().astype(np.float32, copy=False)
+                        part = full if rows_attr is None else shard_of(full, self.world, self.rank)
+                        self.state[name][kind].copy_(torch.from_numpy(part).view_as(self.state[name][kind]))
+                self.arena.tensor("ws")[24:32].view(torch.int64).fill_(step)
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)
+
     def close(self):
         torch.cuda.synchronize(self.device)
         self.arena.close()

@@ -13,7 +13,17 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("BETA_REC_REFERENCE", "/root/reference")
+def _find_reference():
+    """$BETA_REC_REFERENCE, else /root/reference (build container), else baseline/_ref (the git-ignored copy of the
+    reference PACKAGE that travels to the GPU box; written by oracle/install_ref.sh)."""
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for cand in (os.environ.get("BETA_REC_REFERENCE"), "/root/reference", os.path.join(here, "baseline", "_ref")):
+        if cand and os.path.isdir(os.path.join(cand, "beta_rec")):
+            return cand
+    return os.environ.get("BETA_REC_REFERENCE", "/root/reference")
+
+
+REFERENCE_ROOT = _find_reference()
 
 
 def reference_available():

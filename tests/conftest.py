@@ -22,7 +22,8 @@ def pytest_collection_modifyitems(config, items):
         has_gpu = False
     skip_gpu = pytest.mark.skip(reason="no CUDA device")
     skip_ref = pytest.mark.skip(reason="/root/reference not present")
-    has_ref = os.path.isdir(os.path.join(os.environ.get("BETA_REC_REFERENCE", "/root/reference"), "beta_rec"))
+    has_ref = any(os.path.isdir(os.path.join(c, "beta_rec")) for c in
+                  (os.environ.get("BETA_REC_REFERENCE") or "/nonexistent", "/root/reference", os.path.join(ROOT, "baseline", "_ref")))
     for it in items:
         if "gpu" in it.keywords and not has_gpu:
             it.add_marker(skip_gpu)

@@ -184,3 +184,93 @@ def test_route_triples_kernel_is_bit_exact_vs_oracle(world):
         assert np.array_equal(counts.cpu().numpy(), c)
         assert np.array_equal(ou.cpu().numpy(), ru) and np.array_equal(op_.cpu().numpy(), rp)
         assert np.array_equal(on.cpu().numpy(), rn)
+
+
+# --------------------------------------------------------------------------- #
+# sharded checkpoint: save (gather -> reference state_dict) / resume (scatter), optimizer state included
+# --------------------------------------------------------------------------- #
+def _ckpt_worker(rank, world, port, optimizer, q, path):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from beta_recsys_b200.sharded import ShardedMFEngine
+
+        nu, ni, d, bsz, lr = 1003, 499, 64, 512, 0.05
+        rng = np.random.default_rng(11)
+        p = _state(rng, nu, ni, d)
+        batches = [[(_zipf(rng, nu, bsz), _zipf(rng, ni, bsz), rng.integers(0, ni, bsz)) for _ in range(world)] for _ in range(3)]
+        cfg = {"model": dict(device_str="cuda:%d" % rank, n_users=nu, n_items=ni, emb_dim=d, batch_size=bsz,
+                             optimizer=optimizer, lr=lr, loss="bpr", adam_mode="dense")}
+
+        def step(eng, t):
+            return eng.train_single_batch(tuple(torch.from_numpy(x).cuda() for x in batches[t][rank]))
+
+        a = ShardedMFEngine(cfg, state=p)
+        step(a, 0)
+        step(a, 1)
+        a.save_checkpoint(path)
+        step(a, 2)
+        want = a.gather_state()
+        want_opt = a.gather_optimizer_state()
+        a.close()
+        # the file is the reference module's state_dict: keys, shapes, dtypes (models/mf.py:17-30)
+        sd = torch.load(path, map_location="cpu")
+        assert {k: tuple(v.shape) for k, v in sd.items()} == {
+            "global_bias": (1,), "user_emb.weight": (nu, d), "item_emb.weight": (ni, d), "user_bias.weight": (nu, 1),
+            "item_bias.weight": (ni, 1)}
+        assert all(v.dtype == torch.float32 for v in sd.values())
+        b = ShardedMFEngine(cfg)  # fresh random tables
+        b.resume_checkpoint(path)
+        step(b, 2)
+        got, got_opt = b.gather_state(), b.gather_optimizer_state()
+        b.close()
+        for k in want:  # same step from the same state: only the order of fp32 atomics may differ
+            assert np.abs(got[k] - want[k]).max() <= 1e-6 * max(1.0, np.abs(want[k]).max()), k
+        assert set(got_opt) == set(want_opt)
+        for idx in want_opt:
+            assert float(got_opt[idx]["step"]) == float(want_opt[idx]["step"]) == 3.0
+            for name in want_opt[idx]:
+                if name != "step":
+                    assert torch.allclose(got_opt[idx][name], want_opt[idx][name], rtol=1e-5, atol=1e-9), (idx, name)
+        if rank == 0:  # the same file loads into the single-GPU engine
+            from beta_recsys_b200.engines import MFEngine
+
+            c1 = {"model": dict(cfg["model"], device_str="cuda:0"), "system": {"run_dir": "/tmp/brs_test"}}
+            e1 = MFEngine(c1)
+            e1.resume_checkpoint(path)
+            for k, v in e1.model.state_dict().items():
+                assert torch.equal(v.cpu(), sd[k]), k
+        q.put((rank, "ok"))
+    except Exception:  # pragma: no cover
+        import traceback
+
+        q.put((rank, traceback.format_exc()[-1500:]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("world,optimizer", [(1, "adam"), (1, "sgd"), (2, "adam"), (2, "rmsprop")])
+def test_sharded_checkpoint_roundtrip(world, optimizer, tmp_path):
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    port = _free_port()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    os.environ["PYTHONPATH"] = root + os.pathsep + os.environ.get("PYTHONPATH", "")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    path = str(tmp_path / "mf_sharded.ckpt")
+    procs = [ctx.Process(target=_ckpt_worker, args=(r, world, port, optimizer, q, path)) for r in range(world)]
+    saved = sys.path[:]
+    sys.path[:] = [root] + [x for x in saved if x != root]
+    try:
+        for p in procs:
+            p.start()
+    finally:
+        sys.path[:] = saved
+    res = [q.get(timeout=500) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=30)
+    assert sorted(res) == [(r, "ok") for r in range(world)], res
