@@ -77,6 +77,9 @@ def run_reference_train(tmp_path, device, use_install):
 
     cfg = json.loads(json.dumps(MF_DEFAULT))
     cfg["system"]["root_dir"] = str(tmp_path) + "/"
+    # TrainEngine.get_device (core/train_engine.py:37-57): a one-character value is a gpu id -> "cuda:<id>"
+    # (its "cuda:#" branch calls int(":0") and cannot be used); "cpu" stays "cpu"
+    cfg["system"]["device"] = "cpu" if device == "cpu" else device.replace("cuda:", "")
     cfg_file = tmp_path / "mf_default.json"
     cfg_file.write_text(json.dumps(cfg))
     train, valid, test = synthetic_split()

@@ -226,8 +226,13 @@ def _ckpt_worker(rank, world, port, optimizer, q, path):
         step(b, 2)
         got, got_opt = b.gather_state(), b.gather_optimizer_state()
         b.close()
-        for k in want:  # same step from the same state: only the order of fp32 atomics may differ
-            assert np.abs(got[k] - want[k]).max() <= 1e-6 * max(1.0, np.abs(want[k]).max()), k
+        # same step from the same state: only the order of the fp32 gradient atomics may differ -- ~1e-7 relative on
+        # g, which lr * m / (sqrt(v) + eps) amplifies without bound where |g| ~ eps (tests/test_oracle_golden.py), so
+        # the adaptive optimizers get the documented 2e-3 * lr budget and SGD the tight one
+        tol = 1e-6 if optimizer == "sgd" else 2e-3 * lr
+        for k in want:
+            assert np.abs(got[k] - want[k]).max() <= tol * max(1.0, np.abs(want[k]).max()), k
+            assert np.mean(np.abs(got[k] - want[k]) > 1e-6) < 0.01, k  # and only isolated elements use it
         assert set(got_opt) == set(want_opt)
         for idx in want_opt:
             assert float(got_opt[idx]["step"]) == float(want_opt[idx]["step"]) == 3.0
