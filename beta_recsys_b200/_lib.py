@@ -151,6 +151,7 @@ _PROTOTYPES = {
     "brs_lightgcn_scores": (C.c_int, [C.POINTER(LightGCNModel), _P, _P, C.c_int64, _P, _P]),
     "brs_rows_assign": (C.c_int, [C.POINTER(Rowset), _P, C.c_int64, _P, _P]),
     "brs_rows_scatter_grad": (C.c_int, [C.POINTER(Entity), C.c_int32, _P, C.c_int64, _P, C.c_float, _P]),
+    "brs_rows_read_grad": (C.c_int, [C.POINTER(Entity), C.c_int32, _P, C.c_int64, _P, _P]),
     "brs_rows_sgd": (C.c_int, [C.POINTER(Entity), C.c_int32, C.c_double, _P]),
     "brs_rows_adam": (C.c_int, [C.POINTER(Entity), C.c_int32, C.POINTER(Opt), C.c_int64, _P]),
     "brs_dense_adam_sweep": (C.c_int, [C.POINTER(Entity), C.c_int32, C.POINTER(Opt), C.c_int64, _P]),

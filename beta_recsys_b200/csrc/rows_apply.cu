@@ -634,7 +634,43 @@ __global__ void __launch_bounds__(kThreads) rows_scatter_grad_kernel(brs_table t
     }
 }
 
+// out[k, :] = grad_scratch[slot(idx[k])]: the inverse of rows_scatter_grad_kernel (rows without a slot read as 0)
+__global__ void __launch_bounds__(kThreads) rows_read_grad_kernel(brs_table tb, const int* __restrict__ slot_map, int cap,
+                                                                  const long long* __restrict__ idx, long long n,
+                                                                  float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int d = tb.dim;
+    for (long long k = (long long)blockIdx.x * kWarps + (threadIdx.x >> 5); k < n; k += (long long)gridDim.x * kWarps) {
+        const long long row = idx[k];
+        long long slot = -1;
+        if ((unsigned long long)row < (unsigned long long)tb.n_rows) slot = slot_map[row];
+        float* op = out + k * d;
+        if ((d & 3) == 0) {
+            for (int c = lane * 4; c < d; c += 128)
+                *(float4*)(op + c) = slot < 0 ? make_float4(0.f, 0.f, 0.f, 0.f)
+                                              : *(const float4*)(tb.grad + gs_off(d, cap, (unsigned)slot, c));
+        } else {
+            for (int c = lane; c < d; c += 32) op[c] = slot < 0 ? 0.f : tb.grad[slot * d + c];
+        }
+    }
+}
+
 }  // namespace
+
+extern "C" int brs_rows_read_grad(const brs_entity* entity, int32_t table, const int64_t* idx, int64_t n, float* out,
+                                  void* stream) {
+    if (!entity || table < 0 || table >= entity->n_tables || !idx || !out || n < 0) return BRS_ERR_INVALID_ARG;
+    const brs_table& tb = entity->table[table];
+    if (!tb.grad || !entity->rows.slot_map) return BRS_ERR_INVALID_ARG;
+    if (n == 0) return BRS_OK;
+    long long blocks = (n + kWarps - 1) / kWarps;
+    const long long cap = (long long)brs_sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    rows_read_grad_kernel<<<(int)blocks, kThreads, 0, (cudaStream_t)stream>>>(tb, entity->rows.slot_map, entity->rows.capacity,
+                                                                             (const long long*)idx, n, out);
+    BRS_CUDA_CHECK(cudaGetLastError());
+    return BRS_OK;
+}
 
 extern "C" int brs_rows_assign(const brs_rowset* rows, const int64_t* idx, int64_t n, void* ws, void* stream) {
     if (!rows || !ws) return BRS_ERR_INVALID_ARG;

@@ -375,6 +375,11 @@ int brs_rows_assign(const brs_rowset *rows, const int64_t *idx, int64_t n, void 
 /* grad_scratch[slot(idx[k])] += scale * src[k, :]   (src is [n, dim] of entity->table[table]) */
 int brs_rows_scatter_grad(const brs_entity *entity, int32_t table, const int64_t *idx, int64_t n, const float *src,
                           float scale, void *stream);
+/* out[k, :] = grad_scratch[slot(idx[k])] (0 for rows without a slot): reads the accumulated gradient rows back
+ * without applying them -- the row-sharded NeuMF step ships them to the rows' owners, and the parity tests
+ * compare gradients, not only updated parameters */
+int brs_rows_read_grad(const brs_entity *entity, int32_t table, const int64_t *idx, int64_t n, float *out,
+                       void *stream);
 /* touched rows only: p -= lr*g (exactly what torch.optim.SGD does, g = 0 elsewhere) */
 int brs_rows_sgd(const brs_entity *entities, int32_t n_entities, double lr, void *stream);
 /* touched rows only, Adam with explicit step number t (1-based) */

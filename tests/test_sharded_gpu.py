@@ -279,3 +279,92 @@ def test_sharded_checkpoint_roundtrip(world, optimizer, tmp_path):
     for p in procs:
         p.join(timeout=30)
     assert sorted(res) == [(r, "ok") for r in range(world)], res
+
+
+# --------------------------------------------------------------------------- #
+# row-sharded NeuMF (BASELINE configs[2]): every rank its own batch == the oracle on the global batch
+# --------------------------------------------------------------------------- #
+def _neumf_state(rng, nu, ni, emb, nl):
+    w = 2 * emb * 2 ** (nl - 1)
+    st = {"embedding_user_mlp.weight": rng.normal(0, 0.1, (nu, w // 2)), "embedding_item_mlp.weight": rng.normal(0, 0.1, (ni, w // 2)),
+          "embedding_user_mf.weight": rng.normal(0, 0.1, (nu, emb)), "embedding_item_mf.weight": rng.normal(0, 0.1, (ni, emb)),
+          "affine_output.weight": rng.normal(0, 0.3, (1, w // 2 ** nl + emb)), "affine_output.bias": rng.normal(0, 0.1, (1,))}
+    for l in range(nl):
+        st["fc_layers.%d.weight" % (3 * l + 1)] = rng.normal(0, 0.1, (w >> (l + 1), w >> l))
+        st["fc_layers.%d.bias" % (3 * l + 1)] = rng.normal(0, 0.05, (w >> (l + 1),))
+    return {k: v.astype(np.float32) for k, v in st.items()}
+
+
+def _neumf_worker(rank, world, port, optimizer, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from beta_recsys_b200.sharded_ncf import ShardedNeuMFEngine
+
+        nu, ni, emb, nl, bsz, lr = 1003, 499, 16, 2, 256, (0.05 if optimizer == "sgd" else 1e-3)
+        rng = np.random.default_rng(5)
+        p = _neumf_state(rng, nu, ni, emb, nl)
+        steps = 3 if optimizer == "sgd" else 1
+        batches = [[(_zipf(rng, nu, bsz), _zipf(rng, ni, bsz), (rng.random(bsz) < 0.3).astype(np.float32)) for _ in range(world)]
+                   for _ in range(steps)]
+        cfg = {"model": dict(model="ncf_end", device_str="cuda:%d" % rank, n_users=nu, n_items=ni, emb_dim=emb, batch_size=bsz,
+                             optimizer=optimizer, lr=lr, dropout=0.0, adam_mode="dense", mlp_config={"n_layers": nl}),
+               "system": {"run_dir": "/tmp/brs_test"}}
+        import io
+        from contextlib import redirect_stdout
+
+        with redirect_stdout(io.StringIO()):
+            eng = ShardedNeuMFEngine(cfg, state=p)
+        st = O.new_opt_state(p, optimizer)
+        for t in range(steps):
+            loss = eng.train_single_batch(*[torch.from_numpy(x).cuda() for x in batches[t][rank]])
+            g = [np.concatenate([b[c] for b in batches[t]]) for c in range(3)]
+            ol = O.neumf_train_single_batch(p, st, g[0], g[1], g[2], nl, optimizer, lr)
+            assert abs(loss - ol) <= 1e-5 * max(1.0, abs(ol)), (t, loss, ol)
+        got = eng.gather_state()
+        assert set(got) == set(p)
+        for k in p:
+            if optimizer == "sgd":
+                scale = max(np.abs(p[k]).max(), 0.05)
+                err = np.abs(got[k].astype(np.float64) - p[k]).max() / scale
+                assert err <= 2e-5, (k, err)
+            else:  # first Adam step: |dw| <= lr whatever the rounding; compare within the documented budget
+                assert np.abs(got[k].astype(np.float64) - p[k]).max() <= 2e-3 * lr + 1e-7, k
+        with pytest.raises(IndexError):
+            bad = batches[0][rank][0].copy()
+            bad[3] = nu
+            eng.train_single_batch(torch.from_numpy(bad).cuda(), torch.from_numpy(batches[0][rank][1]).cuda(),
+                                   torch.from_numpy(batches[0][rank][2]).cuda())
+        q.put((rank, "ok"))
+    except Exception:  # pragma: no cover
+        import traceback
+
+        q.put((rank, traceback.format_exc()[-1800:]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("world,optimizer", [(1, "sgd"), (1, "adam"), (2, "sgd"), (2, "adam"), (4, "sgd")])
+def test_sharded_neumf_matches_oracle_on_the_global_batch(world, optimizer):
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    port = _free_port()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    os.environ["PYTHONPATH"] = root + os.pathsep + os.environ.get("PYTHONPATH", "")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_neumf_worker, args=(r, world, port, optimizer, q)) for r in range(world)]
+    saved = sys.path[:]
+    sys.path[:] = [root] + [x for x in saved if x != root]
+    try:
+        for p in procs:
+            p.start()
+    finally:
+        sys.path[:] = saved
+    res = [q.get(timeout=500) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=30)
+    assert sorted(res) == [(r, "ok") for r in range(world)], res
