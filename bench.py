@@ -552,7 +552,7 @@ def run_ours(a):
     from beta_recsys_b200.engines import MFEngine
 
     rank, world, local = dist_env()
-    if a.config != 2 and a.gpus != 1:
+    if a.config not in (2, 3) and a.gpus != 1:
         raise SystemExit("--config %d is a single-GPU line (see bench_configs.py); run it with --gpus 1" % a.config)
     if world != a.gpus:
         if a.gpus == 1:
@@ -565,6 +565,18 @@ def run_ours(a):
         import torch.distributed as dist
 
         dist.init_process_group("nccl", device_id=dev)
+        if a.config == 3:
+            import bench_configs as bc
+
+            sampler = ClockSampler(local)
+            sampler.start()
+            peak, peak_src = measured_peak()
+            line = bc.run_neumf_sharded(a, rank, world, local, dev, sampler, (peak, peak_src, measured_tflops()))
+            sampler.stop()
+            if line is not None:
+                print(json.dumps(line))
+            dist.destroy_process_group()
+            return
         return run_sharded(a, rank, world, local, dev)
     lib = _lib.load()
     if a.config != 2:

@@ -127,6 +127,75 @@ def run_neumf(a, dev, sampler, peak):
                       None, {"cpu_baseline_fn": "neumf"})
 
 
+def run_neumf_sharded(a, rank, world, local, dev, sampler, peak):
+    """configs[2] as BASELINE states it: NeuMF with the four embedding tables row-sharded over the ranks
+    (beta_recsys_b200/sharded_ncf.py), every rank feeding its own batch; weak scaling."""
+    import torch.distributed as dist
+
+    from beta_recsys_b200.sharded_ncf import ShardedNeuMFEngine
+
+    hbm_peak, peak_src, tf_peak = peak
+    nu, ni, emb, nl, b = a.users, a.items, 64, 3, a.batch
+    cfg = {"model": dict(model="ncf_end", device_str=str(dev), n_users=nu, n_items=ni, emb_dim=emb, batch_size=b,
+                         optimizer="adam", lr=1e-3, dropout=0.0, adam_mode=a.adam_mode, mlp_config={"n_layers": nl}),
+           "system": {"run_dir": "/tmp/brs_bench"}}
+    with redirect_stdout(io.StringIO()):
+        eng = ShardedNeuMFEngine(cfg)
+    g = torch.Generator(device=dev)
+    g.manual_seed(SEED + rank)
+    nb = 8
+    u = _zipf(nu, 1.05, g, dev)(nb * b)
+    i = _zipf(ni, 1.05, g, dev)(nb * b)
+    r = (torch.rand(nb * b, generator=g, device=dev) < 0.2).float()
+    k = [0]
+
+    def step():
+        s = slice((k[0] % nb) * b, (k[0] % nb + 1) * b)
+        k[0] += 1
+        return eng.train_single_batch(u[s], i[s], r[s])
+
+    steps = min(a.steps, 40)
+    for _ in range(3):
+        step()
+    dist.barrier()
+    torch.cuda.synchronize(dev)
+    e0, e1 = _events(None)
+    t0 = time.time()
+    e0.record()
+    for _ in range(steps):
+        loss = step()
+    e1.record()
+    dist.barrier()
+    torch.cuda.synchronize(dev)
+    ms = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device=dev)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = ms.item()
+    while time.time() - t0 < 1.2:
+        step()
+    clocks = sampler.summary(t0, time.time())
+    if rank != 0:
+        return None
+    w = 2 * emb * 2 ** (nl - 1)
+    row_floats = 2 * (w // 2 + emb)
+    nvl = 2.0 * (world - 1) / world * b * row_floats * 4  # rows in + gradient rows out, per direction per rank
+    step_s = ms * 1e-3
+    roof = {"bound": "nvlink", "kernel": "NCCL all-to-all of embedding rows (forward) and gradient rows (backward)",
+            "achieved": nvl / step_s / 1e9, "peak": 770.0, "unit": "GB/s", "frac": nvl / step_s / 1e9 / 770.0,
+            "peak_source": "B200_PROFILING.md measured peer copy, per direction per GPU", "traffic": None,
+            "note": "bytes that must cross NVLink per rank, step and direction (remote fraction x batch x %d row floats x 4 B, "
+                    "forward + backward) / whole-step time" % row_floats}
+    config = {"workload": "configs[2]: NeuMF %dM users x %dM items, emb_dim=64, MLP=[256,128,64], embeddings row-sharded over %d "
+                          "B200, batch=%d per rank" % (nu // 1_000_000, ni // 1_000_000, world, b),
+              "n_users": nu, "n_items": ni, "emb_dim": emb, "batch_per_gpu": b, "global_batch": b * world, "optimizer": "adam",
+              "optimizer_mode": a.adam_mode, "lr": 1e-3, "parallelism": "embedding rows sharded x%d (owner = row mod N), tower replicated"
+              % world}
+    line = _base_line(a, "BCE interactions/sec (NeuMF)", "interactions/s", b * world / step_s, ms, config, roof, clocks, None, None,
+                      {"final_loss": loss})
+    line["n_gpus"] = world
+    line["steps"] = steps
+    return line
+
+
 # --------------------------------------------------------------------------- #
 # config 4: LightGCN (beta_rec/models/lightgcn.py), 3 layers, dim 64, keep_pro 0.6
 # --------------------------------------------------------------------------- #
