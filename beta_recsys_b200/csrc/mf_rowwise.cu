@@ -456,7 +456,10 @@ __device__ __forceinline__ float transpose_reduce(float (&v)[NV], int lane) {
 }
 
 
-constexpr int kRowWarps = 8;  // warps (= work units) per CTA of the row kernels
+#ifndef BRS_ROW_WARPS
+#define BRS_ROW_WARPS 4
+#endif
+constexpr int kRowWarps = BRS_ROW_WARPS;  // warps (= work units) per CTA of the row kernels
 constexpr int kRowThreads = kRowWarps * 32;
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg((const float4*)p); }
@@ -508,28 +511,27 @@ __global__ void __launch_bounds__(kRowThreads) mf_user_rows_kernel(const RowArgs
         // per-lane constants of the gathers
         const float* ue_l = a.ue.w + lane * 4;
         const float* ie_l = a.ie.w + lane * 4;
-        const float* btab = lane == 0 ? a.ub.w : a.ib.w;
         bool colv[VPL];
 #pragma unroll
         for (int v = 0; v < VPL; ++v) colv[v] = FULL || (v * 32 + lane) * 4 < D;
+        const int kl = lane >> KSH;  // the sample of a block whose scalar work (biases, loss chain) this lane does
         // state of the row part being accumulated
         float4 ru[VPL], acc[VPL];
         float uu = 0.f, bu = 0.f, gbias = 0.f;
         int n_row = 0;
+        bool fresh = true;  // warp-uniform: the next sample is the first of a row part (unit start / after a flush)
 #pragma unroll
         for (int v = 0; v < VPL; ++v) ru[v] = acc[v] = f4_zero();
 
         for (int p0 = lo; p0 < hi; p0 += K) {  // warp-uniform
             const int cnt = min(K, hi - p0);
             const int t0 = p0 - base;
-            // ---- load: every row of the block is in flight before the first one is used
+            // ---- load: every row of the block is in flight before the first one is used.  The user row is
+            // loaded with EVERY sample (consecutive samples of a user hit L1): no per-sample "row changed?"
+            // register shuffling in the dot phase
             float4 ir[K][VPL], jr[C == 2 ? K : 1][VPL], ur[K][VPL];
-            float bb[K];
-            bool first[K];
 #pragma unroll
             for (int k = 0; k < K; ++k) {
-                first[k] = false;
-                bb[k] = 0.f;
 #pragma unroll
                 for (int v = 0; v < VPL; ++v) {
                     ir[k][v] = ur[k][v] = f4_zero();
@@ -537,49 +539,37 @@ __global__ void __launch_bounds__(kRowThreads) mf_user_rows_kernel(const RowArgs
                 }
                 if (k < cnt) {  // warp-uniform
                     const int4 ra = tl[t0 + k][0];
-                    const int sb = tl[t0 + k][1].z;
-                    first[k] = p0 + k == sb || p0 + k == lo;  // the user row is read at the first sample of a part
                     const float* ip = ie_l + (size_t)(unsigned)ra.z * (unsigned)D;
                     const float* jp = ie_l + (size_t)(unsigned)(C == 2 ? ra.w : 0) * (unsigned)D;
                     const float* up = ue_l + (size_t)(unsigned)ra.x * (unsigned)D;
 #pragma unroll
                     for (int v = 0; v < VPL; ++v) {
                         if (colv[v]) {
+                            ur[k][v] = ldg4(up + v * 128);
                             ir[k][v] = ldg4(ip + v * 128);
                             if (C == 2) jr[k][v] = ldg4(jp + v * 128);
-                            if (first[k]) ur[k][v] = ldg4(up + v * 128);
                         }
                     }
-                    // lane 0: user bias, lane 1: pos-item bias, lane 2: neg-item bias
-                    const int bi_ = lane == 0 ? ra.x : (lane == 1 ? ra.z : ra.w);
-                    if (lane == 0 ? first[k] : lane <= C) bb[k] = __ldg(btab + (unsigned)bi_);
                 }
             }
+            // the lane group of sample kl loads that sample's three biases (one address per group)
+            const bool onl = kl < cnt;
+            const int4 la = tl[t0 + (onl ? kl : 0)][0], lb = tl[t0 + (onl ? kl : 0)][1];
+            const float b_u = __ldg(a.ub.w + (unsigned)la.x);
+            const float b_i = __ldg(a.ib.w + (unsigned)la.z);
+            const float b_j = (C == 2) ? __ldg(a.ib.w + (unsigned)la.w) : 0.f;
             // ---- phase 1: partial dots
             float dots[K * C];
-            {
-                float4 r1[VPL];
-                float bu1 = bu;
 #pragma unroll
-                for (int v = 0; v < VPL; ++v) r1[v] = ru[v];
+            for (int k = 0; k < K; ++k) {
+                float dp = 0.f, dn = 0.f;
 #pragma unroll
-                for (int k = 0; k < K; ++k) {
-                    if (first[k]) {
-#pragma unroll
-                        for (int v = 0; v < VPL; ++v) r1[v] = ur[k][v];
-                        bu1 = bb[k];  // meaningful on lane 0 only
-                    }
-                    float dp = 0.f, dn = 0.f;
-#pragma unroll
-                    for (int v = 0; v < VPL; ++v) {
-                        dp += f4_dot(r1[v], ir[k][v]);
-                        if (C == 2) dn += f4_dot(r1[v], jr[k][v]);
-                    }
-                    // every bias enters the score through the lane that loaded it
-                    const float ub_ = bu1 + bg;
-                    dots[C * k] = dp + (lane == 0 ? ub_ : (lane == 1 ? bb[k] : 0.f));
-                    if (C == 2) dots[C * k + 1] = dn + (lane == 0 ? ub_ : (lane == 2 ? bb[k] : 0.f));
+                for (int v = 0; v < VPL; ++v) {
+                    dp += f4_dot(ur[k][v], ir[k][v]);
+                    if (C == 2) dn += f4_dot(ur[k][v], jr[k][v]);
                 }
+                dots[C * k] = dp;
+                if (C == 2) dots[C * k + 1] = dn;
             }
             // ---- phase 2: one reduction, one loss chain per block; lanes [k << KSH, (k+1) << KSH) work on sample k
             float z = transpose_reduce<K * C>(dots, lane);
@@ -590,9 +580,8 @@ __global__ void __launch_bounds__(kRowThreads) mf_user_rows_kernel(const RowArgs
                 zp = odd ? other : z;
                 zn = odd ? z : other;
             }
-            const int kl = lane >> KSH;
-            const bool onl = kl < cnt;
-            const int4 la = tl[t0 + (onl ? kl : 0)][0], lb = tl[t0 + (onl ? kl : 0)][1];
+            zp += b_u + b_i + bg;
+            zn += b_u + b_j + bg;
             const float rating = (C == 1) ? __int_as_float(la.w) : 0.f;
             float cu_i, cu_j, loss_k;
             mf_sample_coef_fast<LOSS>(zp, zn, rating, a.inv_b, cu_i, cu_j, loss_k);
@@ -610,7 +599,9 @@ __global__ void __launch_bounds__(kRowThreads) mf_user_rows_kernel(const RowArgs
                     const float ci = __shfl_sync(BRS_FULL_MASK, cu_i, k << KSH);
                     const float cj = (C == 2) ? __shfl_sync(BRS_FULL_MASK, cu_j, k << KSH) : 0.f;
                     const int p = p0 + k;
-                    if (first[k]) {  // a new row part starts here: its PRE-step weights stay in registers
+                    const int4 rb = tl[t0 + k][1];
+                    if (fresh) {  // a new row part starts here: its PRE-step weights stay in registers
+                        fresh = false;
                         uu = 0.f;
 #pragma unroll
                         for (int v = 0; v < VPL; ++v) {
@@ -618,7 +609,7 @@ __global__ void __launch_bounds__(kRowThreads) mf_user_rows_kernel(const RowArgs
                             uu += f4_dot(ru[v], ru[v]);
                             acc[v] = f4_zero();
                         }
-                        bu = bb[k];
+                        bu = __shfl_sync(BRS_FULL_MASK, b_u, k << KSH);
                         gbias = 0.f;
                         n_row = 0;
                     }
@@ -629,7 +620,6 @@ __global__ void __launch_bounds__(kRowThreads) mf_user_rows_kernel(const RowArgs
                     }
                     gbias += ci + cj;
                     n_row += 1;
-                    const int4 rb = tl[t0 + k][1];
                     if (p + 1 == rb.w || p + 1 == hi) {  // last sample of this row inside my unit
                         const int4 ra = tl[t0 + k][0];
                         // regularizer numerator (mf.py:49-54): every forward call of every sample adds |u|^2 + b_u^2
@@ -642,6 +632,7 @@ __global__ void __launch_bounds__(kRowThreads) mf_user_rows_kernel(const RowArgs
                         }
                         flush_row<VPL, FULL, KIND>(a.ue, a.ub, a.pv.u_ticket, a.u_slot_map, a.user_stage, lane, D, skip,
                                                    a.release, os, ra.y, ra.x, row_parts(rb.z, rb.w), ru, acc, bu, gbias);
+                        fresh = true;  // the next sample starts a new row part
                     }
                 }
             }
@@ -679,8 +670,11 @@ __global__ void __launch_bounds__(kRowThreads) mf_user_rows_kernel(const RowArgs
 // the update applied in place.  The last block to finish applies the global-bias step and publishes
 // brs_step_out.
 template <int VPL, bool FULL, int KIND>
-__global__ void __launch_bounds__(kRowThreads) mf_item_rows_kernel(const RowArgs a) {
-    constexpr int K = 8;
+__global__ void __launch_bounds__(kRowThreads, 24 / kRowWarps) mf_item_rows_kernel(const RowArgs a) {
+#ifndef BRS_ITEMS_K
+#define BRS_ITEMS_K 4
+#endif
+    constexpr int K = BRS_ITEMS_K;  // entries per block
     __shared__ int4 s_ia[kRowWarps][kTile];    // i_a of stream position base + t
     __shared__ float2 s_pr[kRowWarps][kTile];  // {coefficient, user slot}
     __shared__ OptScalars s_opt;
@@ -728,61 +722,51 @@ __global__ void __launch_bounds__(kRowThreads) mf_item_rows_kernel(const RowArgs
             // every row of the block is in flight before the first one is used: the staged user row of each
             // entry and, where a row part ends, the item's own row and bias (no dependent load at the flush)
             float4 rr[K][VPL], wr[K][VPL];
-            float wb[K];
+            float wb[K], coef[K];
+            int4 ia[K];
 #pragma unroll
             for (int k = 0; k < K; ++k) {
-                wb[k] = 0.f;
-#pragma unroll
-                for (int v = 0; v < VPL; ++v) rr[k][v] = wr[k][v] = f4_zero();
                 if (k < cnt) {  // warp-uniform
-                    const float* up = us_l + (size_t)(unsigned)__float_as_int(tp[t0 + k].y) * (unsigned)D;
-                    const int4 ia = ta[t0 + k];
-                    const bool last = q0 + k + 1 == ia.w || q0 + k + 1 == hi;
-                    const float* ip = ie_l + (size_t)(unsigned)ia.x * (unsigned)D;
+                    const float2 pr = tp[t0 + k];
+                    coef[k] = pr.x;
+                    ia[k] = ta[t0 + k];
+                    const float* up = us_l + (size_t)(unsigned)__float_as_int(pr.y) * (unsigned)D;
 #pragma unroll
-                    for (int v = 0; v < VPL; ++v) {
-                        if (colv[v]) {
-                            rr[k][v] = ldg4(up + v * 128);
-                            if (last) wr[k][v] = ld4(ip + v * 128);
-                        }
+                    for (int v = 0; v < VPL; ++v) rr[k][v] = colv[v] ? ldg4(up + v * 128) : f4_zero();
+                    if (q0 + k + 1 == ia[k].w || q0 + k + 1 == hi) {  // warp-uniform: a row part ends with this entry
+                        const float* ip = ie_l + (size_t)(unsigned)ia[k].x * (unsigned)D;
+#pragma unroll
+                        for (int v = 0; v < VPL; ++v) wr[k][v] = colv[v] ? ld4(ip + v * 128) : f4_zero();
+                        wb[k] = a.ib.w[(unsigned)ia[k].x];
                     }
-                    if (last) wb[k] = a.ib.w[(unsigned)ia.x];
                 }
             }
 #pragma unroll
             for (int k = 0; k < K; ++k) {
                 if (k < cnt) {  // warp-uniform
-                    const int q = q0 + k;
-                    const int4 ia = ta[t0 + k];
-                    const float coef = tp[t0 + k].x;
-                    if (q == ia.z || q == lo) {
 #pragma unroll
-                        for (int v = 0; v < VPL; ++v) acc[v] = f4_zero();
-                        gbias = 0.f;
-                        n_row = 0;
-                    }
-#pragma unroll
-                    for (int v = 0; v < VPL; ++v) acc[v] = f4_fma(coef, rr[k][v], acc[v]);
-                    gbias += coef;
+                    for (int v = 0; v < VPL; ++v) acc[v] = f4_fma(coef[k], rr[k][v], acc[v]);
+                    gbias += coef[k];
                     n_row += 1;
-                    if (q + 1 == ia.w || q + 1 == hi) {
-                        float4 w[VPL];
+                    if (q0 + k + 1 == ia[k].w || q0 + k + 1 == hi) {
                         float ww = 0.f;
 #pragma unroll
-                        for (int v = 0; v < VPL; ++v) {
-                            w[v] = wr[k][v];
-                            ww += f4_dot(w[v], w[v]);
-                        }
+                        for (int v = 0; v < VPL; ++v) ww += f4_dot(wr[k][v], wr[k][v]);
                         const float bi = wb[k];
                         reg_acc += (float)n_row * (ww + (lane == 0 ? bi * bi : 0.f));  // mf.py:49-54, item side
                         if (a.reg_w != 0.f) {
                             const float nl = (float)n_row * rw;
 #pragma unroll
-                            for (int v = 0; v < VPL; ++v) acc[v] = f4_fma(nl, w[v], acc[v]);
+                            for (int v = 0; v < VPL; ++v) acc[v] = f4_fma(nl, wr[k][v], acc[v]);
                             gbias += nl * bi;
                         }
                         flush_row<VPL, FULL, KIND>(a.ie, a.ib, a.pv.i_ticket, a.i_slot_map, nullptr, lane, D, skip, a.release,
-                                                   os, ia.y, ia.x, row_parts(ia.z, ia.w), w, acc, bi, gbias);
+                                                   os, ia[k].y, ia[k].x, row_parts(ia[k].z, ia[k].w), wr[k], acc, bi, gbias);
+                        // the next entry starts a new row part
+#pragma unroll
+                        for (int v = 0; v < VPL; ++v) acc[v] = f4_zero();
+                        gbias = 0.f;
+                        n_row = 0;
                     }
                 }
             }
