@@ -147,6 +147,8 @@ _PROTOTYPES = {
     "brs_spmm_csr": (C.c_int, [C.POINTER(Csr), _P, C.c_float, _P, _P, C.c_int32, _P]),
     "brs_lightgcn_propagate": (C.c_int, [C.POINTER(LightGCNModel), _P, C.c_float, _P]),
     "brs_lightgcn_fwd_bwd": (C.c_int, [C.POINTER(LightGCNModel), _P, C.c_float, _P, _P, _P, C.c_int64, _P]),
+    "brs_lightgcn_tail": (C.c_int, [C.POINTER(LightGCNModel), _P, _P, _P, C.c_int64, C.c_int64, _P]),
+    "brs_lightgcn_reg_grad": (C.c_int, [C.POINTER(LightGCNModel), _P, _P, _P, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _P, _P]),
     "brs_lightgcn_apply": (C.c_int, [C.POINTER(LightGCNModel), C.POINTER(Opt), C.c_int64, _P, _P]),
     "brs_lightgcn_scores": (C.c_int, [C.POINTER(LightGCNModel), _P, _P, C.c_int64, _P, _P]),
     "brs_rows_assign": (C.c_int, [C.POINTER(Rowset), _P, C.c_int64, _P, _P]),

@@ -179,6 +179,7 @@ struct TailArgs {
     float* scores;   // predict
     brs_step_ws* ws;
     int train;
+    long long row_lo, row_hi;  // lightgcn_reg_grad_kernel: only node rows in [row_lo, row_hi) (row_hi == 0: all rows)
 };
 
 // one warp per sample; lanes own float4 columns (D <= 512)
@@ -269,10 +270,13 @@ __global__ void __launch_bounds__(kThreads) lightgcn_reg_grad_kernel(const TailA
         const long long id = which == 0 ? a.users[s] : (which == 1 ? a.pos[s] : a.neg[s]);
         const long long lim = which == 0 ? a.n_users : a.n_items;
         if ((unsigned long long)id >= (unsigned long long)lim) continue;
-        const size_t r = (size_t)(which == 0 ? id : a.n_users + id) * D;
+        const long long node = which == 0 ? id : a.n_users + id;
+        if (a.row_hi > 0 && (node < a.row_lo || node >= a.row_hi)) continue;  // another rank owns this row
+        const size_t r = (size_t)node * D;
+        float* gr = g + (size_t)(node - (a.row_hi > 0 ? a.row_lo : 0)) * D;
         for (int c = lane * 4; c < D; c += 128) {
             const float4 x = ld_row4(a.emb[0] + r + c);
-            red_add4(g + r + c, make_float4(k * x.x, k * x.y, k * x.z, k * x.w));
+            red_add4(gr + c, make_float4(k * x.x, k * x.y, k * x.z, k * x.w));
         }
     }
 }
@@ -379,6 +383,57 @@ extern "C" int brs_lightgcn_fwd_bwd(const brs_lightgcn_model* m, const uint8_t* 
         cur = out;
     }
     lightgcn_reg_grad_kernel<<<warp_grid(3 * batch, (const void*)lightgcn_reg_grad_kernel), kThreads, 0, st>>>(t, m->param.grad);
+    BRS_CUDA_CHECK(cudaGetLastError());
+    return BRS_OK;
+}
+
+// ---- pieces of brs_lightgcn_fwd_bwd for the row-partitioned multi-GPU step (sharded_lightgcn.py), which runs the
+// propagate and its backward as per-rank block SpMMs (brs_spmm_csr) with collectives in between
+static void tail_args(const brs_lightgcn_model* m, const int64_t* users, const int64_t* pos_items, const int64_t* neg_items,
+                      int64_t batch, int64_t global_batch, TailArgs& t) {
+    memset(&t, 0, sizeof(t));
+    for (int l = 0; l <= m->n_layers; ++l) t.emb[l] = m->emb[l];
+    t.n_layers = m->n_layers;
+    t.n_users = m->n_users;
+    t.n_items = m->n_items;
+    t.dim = m->dim;
+    t.users = (const long long*)users;
+    t.pos = (const long long*)pos_items;
+    t.neg = (const long long*)neg_items;
+    t.batch = batch;
+    t.inv_b = 1.0f / (float)global_batch;
+    t.decay = m->decay;
+    t.inv_lp1 = 1.0f / (float)(m->n_layers + 1);
+    t.d = m->d;
+    t.ws = (brs_step_ws*)m->ws;
+    t.train = 1;
+}
+
+extern "C" int brs_lightgcn_tail(const brs_lightgcn_model* m, const int64_t* users, const int64_t* pos_items,
+                                 const int64_t* neg_items, int64_t batch, int64_t global_batch, void* stream) {
+    int rc = check(m);
+    if (rc != BRS_OK) return rc;
+    if (!users || !pos_items || !neg_items || batch <= 0 || global_batch < batch) return BRS_ERR_INVALID_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    TailArgs t;
+    tail_args(m, users, pos_items, neg_items, batch, global_batch, t);
+    BRS_CUDA_CHECK(cudaMemsetAsync(m->d, 0, (size_t)(m->n_users + m->n_items) * m->dim * sizeof(float), st));
+    lightgcn_tail_kernel<<<warp_grid(batch, (const void*)lightgcn_tail_kernel), kThreads, 0, st>>>(t);
+    BRS_CUDA_CHECK(cudaGetLastError());
+    return BRS_OK;
+}
+
+extern "C" int brs_lightgcn_reg_grad(const brs_lightgcn_model* m, const int64_t* users, const int64_t* pos_items,
+                                     const int64_t* neg_items, int64_t batch, int64_t global_batch, int64_t row_lo,
+                                     int64_t row_hi, float* grad_rows, void* stream) {
+    int rc = check(m);
+    if (rc != BRS_OK) return rc;
+    if (!users || !pos_items || !neg_items || batch <= 0 || !grad_rows || row_lo < 0 || row_hi <= row_lo) return BRS_ERR_INVALID_ARG;
+    TailArgs t;
+    tail_args(m, users, pos_items, neg_items, batch, global_batch, t);
+    t.row_lo = row_lo;
+    t.row_hi = row_hi;
+    lightgcn_reg_grad_kernel<<<warp_grid(3 * batch, (const void*)lightgcn_reg_grad_kernel), kThreads, 0, (cudaStream_t)stream>>>(t, grad_rows);
     BRS_CUDA_CHECK(cudaGetLastError());
     return BRS_OK;
 }

@@ -361,6 +361,17 @@ int brs_lightgcn_propagate(const brs_lightgcn_model *model, const uint8_t *keep_
 int brs_lightgcn_fwd_bwd(const brs_lightgcn_model *model, const uint8_t *keep_mask, float keep_prob,
                          const int64_t *users, const int64_t *pos_items, const int64_t *neg_items, int64_t batch,
                          void *stream);
+/* The two non-SpMM pieces of brs_lightgcn_fwd_bwd, for the row-partitioned multi-GPU step (the propagate and its
+ * backward then run as per-rank block products with brs_spmm_csr and collectives in between):
+ * brs_lightgcn_tail: softplus-BPR + L2 tail of `batch` samples on the layer buffers emb[0..L] (lightgcn.py:171-191),
+ *   scaled for a mean over global_batch; clears d [N, dim] and scatters d loss / d E^(l) into it; loss sum -> ws;
+ * brs_lightgcn_reg_grad: the L2 term's gradient on the layer-0 rows of the batch, restricted to node rows
+ *   [row_lo, row_hi) and added into grad_rows [(row_hi - row_lo), dim] (row 0 = node row_lo). */
+int brs_lightgcn_tail(const brs_lightgcn_model *model, const int64_t *users, const int64_t *pos_items,
+                      const int64_t *neg_items, int64_t batch, int64_t global_batch, void *stream);
+int brs_lightgcn_reg_grad(const brs_lightgcn_model *model, const int64_t *users, const int64_t *pos_items,
+                          const int64_t *neg_items, int64_t batch, int64_t global_batch, int64_t row_lo, int64_t row_hi,
+                          float *grad_rows, void *stream);
 /* optimizer.step() over all rows + loss.item() (lightgcn.py:150-151) */
 int brs_lightgcn_apply(const brs_lightgcn_model *model, const brs_opt *opt, int64_t batch,
                        float *out /* brs_step_out */, void *stream);

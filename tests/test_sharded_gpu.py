@@ -368,3 +368,83 @@ def test_sharded_neumf_matches_oracle_on_the_global_batch(world, optimizer):
     for p in procs:
         p.join(timeout=30)
     assert sorted(res) == [(r, "ok") for r in range(world)], res
+
+
+# --------------------------------------------------------------------------- #
+# row-partitioned LightGCN (BASELINE configs[3]): every rank its own batch == the oracle on the global batch
+# --------------------------------------------------------------------------- #
+def _lightgcn_worker(rank, world, port, optimizer, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from beta_recsys_b200.sharded_lightgcn import ShardedLightGCNEngine
+
+        nu, ni, d, L, n_e, bsz, decay, keep = 1501, 733, 64, 3, 30000, 512, 1e-4, 0.6
+        lr = 0.05 if optimizer == "sgd" else 0.01
+        rng = np.random.default_rng(9)
+        pu, pi = np.arange(1, nu + 1) ** -1.0, np.arange(1, ni + 1) ** -1.0
+        eu, ei = rng.choice(nu, n_e, p=pu / pu.sum()), rng.choice(ni, n_e, p=pi / pi.sum())
+        adj = O.row_normalised_adj(nu, ni, eu, ei)
+        coo = adj.tocoo()
+        tadj = torch.sparse_coo_tensor(torch.from_numpy(np.vstack([coo.row, coo.col]).astype(np.int64)),
+                                       torch.from_numpy(coo.data.astype(np.float32)), (nu + ni, nu + ni))
+        p = {"user_embedding.weight": rng.normal(0, 0.1, (nu, d)).astype(np.float32),
+             "item_embedding.weight": rng.normal(0, 0.1, (ni, d)).astype(np.float32)}
+        cfg = {"model": dict(device_str="cuda:%d" % rank, n_users=nu, n_items=ni, emb_dim=d, layer_size=[d] * L, batch_size=bsz,
+                             optimizer=optimizer, lr=lr, regs=[decay], keep_pro=keep, norm_adj=tadj)}
+        eng = ShardedLightGCNEngine(cfg, state=p)
+        st = O.new_opt_state(p, optimizer)
+        steps = 2 if optimizer == "sgd" else 1
+        for t in range(steps):
+            batches = [(rng.integers(0, nu, bsz), rng.integers(0, ni, bsz), rng.integers(0, ni, bsz)) for _ in range(world)]
+            mask = rng.random(adj.nnz) < keep
+            loss = eng.train_single_batch(tuple(torch.from_numpy(x).cuda() for x in batches[rank]), keep_mask=mask.astype(np.uint8))
+            g = [np.concatenate([b[c] for b in batches]) for c in range(3)]
+            ol = O.lightgcn_train_single_batch(p, st, O.edge_dropout(adj, mask, keep), g[0], g[1], g[2], L, decay,
+                                               optimizer=optimizer, lr=lr)
+            assert abs(loss - ol) <= 1e-5 * max(1, abs(ol)), (t, loss, ol)
+        got = eng.gather_state()
+        for k in p:
+            if optimizer == "sgd":
+                err = np.abs(got[k].astype(np.float64) - p[k]).max() / max(np.abs(p[k]).max(), 1e-30)
+                assert err <= 1e-5, (k, err)
+            else:
+                assert np.abs(got[k].astype(np.float64) - p[k]).max() <= 2e-3 * lr + 1e-7, k
+        # the device-drawn mask is the same on every rank (same seed, same generator state)
+        m = eng.draw_keep_mask()
+        ms = [torch.empty_like(m) for _ in range(world)]
+        dist.all_gather(ms, m)
+        assert all(torch.equal(ms[0], x) for x in ms)
+        q.put((rank, "ok"))
+    except Exception:  # pragma: no cover
+        import traceback
+
+        q.put((rank, traceback.format_exc()[-1800:]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("world,optimizer", [(1, "sgd"), (1, "adam"), (2, "sgd"), (2, "adam"), (4, "sgd")])
+def test_sharded_lightgcn_matches_oracle_on_the_global_batch(world, optimizer):
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    port = _free_port()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    os.environ["PYTHONPATH"] = root + os.pathsep + os.environ.get("PYTHONPATH", "")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_lightgcn_worker, args=(r, world, port, optimizer, q)) for r in range(world)]
+    saved = sys.path[:]
+    sys.path[:] = [root] + [x for x in saved if x != root]
+    try:
+        for p in procs:
+            p.start()
+    finally:
+        sys.path[:] = saved
+    res = [q.get(timeout=500) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=30)
+    assert sorted(res) == [(r, "ok") for r in range(world)], res
