@@ -76,6 +76,8 @@ def parse():
         a.users, a.items = a.users or 10_000_000, a.items or 1_000_000
         if a.adam_mode == "dense" and "--adam-mode" not in sys.argv:
             a.adam_mode = "touched"  # the reference-exact dense sweep streams 42 GB per step; named in the line
+    elif a.config == 4:
+        a.users, a.items = a.users or N_USERS, a.items or N_ITEMS
     elif a.gpus > 1:  # the scaling target is stated on 10M x 1M row-sharded tables
         a.users, a.items = a.users or 10_000_000, a.items or 1_000_000
     else:
@@ -552,7 +554,7 @@ def run_ours(a):
     from beta_recsys_b200.engines import MFEngine
 
     rank, world, local = dist_env()
-    if a.config not in (2, 3) and a.gpus != 1:
+    if a.config not in (2, 3, 4) and a.gpus != 1:
         raise SystemExit("--config %d is a single-GPU line (see bench_configs.py); run it with --gpus 1" % a.config)
     if world != a.gpus:
         if a.gpus == 1:
@@ -565,13 +567,14 @@ def run_ours(a):
         import torch.distributed as dist
 
         dist.init_process_group("nccl", device_id=dev)
-        if a.config == 3:
+        if a.config in (3, 4):
             import bench_configs as bc
 
             sampler = ClockSampler(local)
             sampler.start()
             peak, peak_src = measured_peak()
-            line = bc.run_neumf_sharded(a, rank, world, local, dev, sampler, (peak, peak_src, measured_tflops()))
+            fn = bc.run_neumf_sharded if a.config == 3 else bc.run_lightgcn_sharded
+            line = fn(a, rank, world, local, dev, sampler, (peak, peak_src, measured_tflops()))
             sampler.stop()
             if line is not None:
                 print(json.dumps(line))

@@ -267,6 +267,76 @@ def run_lightgcn(a, dev, sampler, peak):
                       config, roof, clocks, e2e, None, {"cpu_baseline_fn": "lightgcn", "graph_steps_per_s": 1.0 / step_s})
 
 
+def run_lightgcn_sharded(a, rank, world, local, dev, sampler, peak):
+    """configs[3] as BASELINE states it: LightGCN with the node rows partitioned over the ranks
+    (beta_recsys_b200/sharded_lightgcn.py), every rank feeding its own batch."""
+    import torch.distributed as dist
+
+    from beta_recsys_b200 import graph
+    from beta_recsys_b200.sharded_lightgcn import ShardedLightGCNEngine
+
+    hbm_peak, peak_src, _ = peak
+    nu, ni, d, L, b = a.users, a.items, 64, 3, a.batch
+    g = torch.Generator(device=dev)
+    g.manual_seed(SEED)  # the same graph on every rank
+    eu = _zipf(nu, 0.8, g, dev)(a.edges)
+    ei = _zipf(ni, 0.8, g, dev)(a.edges)
+    adj = graph.build_norm_adj(eu, ei, nu, ni, device=dev)
+    cfg = {"model": dict(device_str=str(dev), n_users=nu, n_items=ni, emb_dim=d, batch_size=b, optimizer="adam", lr=0.05,
+                         regs=[1e-5], keep_pro=0.6, layer_size=[d] * L, norm_adj=adj)}
+    eng = ShardedLightGCNEngine(cfg)
+    g.manual_seed(SEED + 1 + rank)
+    u = torch.randint(0, nu, (8 * b,), generator=g, device=dev)
+    i = torch.randint(0, ni, (8 * b,), generator=g, device=dev)
+    j = torch.randint(0, ni, (8 * b,), generator=g, device=dev)
+    k = [0]
+
+    def step():
+        s = slice((k[0] % 8) * b, (k[0] % 8 + 1) * b)
+        k[0] += 1
+        return eng.train_single_batch((u[s], i[s], j[s]))
+
+    steps = min(a.steps, 30)
+    for _ in range(3):
+        step()
+    dist.barrier()
+    torch.cuda.synchronize(dev)
+    e0, e1 = _events(None)
+    t0 = time.time()
+    e0.record()
+    for _ in range(steps):
+        loss = step()
+    e1.record()
+    dist.barrier()
+    torch.cuda.synchronize(dev)
+    ms = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device=dev)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = ms.item()
+    while time.time() - t0 < 1.2:
+        step()
+    clocks = sampler.summary(t0, time.time())
+    if rank != 0:
+        return None
+    n, nnz = nu + ni, adj.nnz
+    step_s = ms * 1e-3
+    coll = (2 * L + 1) * (world - 1) / world * n * d * 4  # bytes a rank receives per step (all-gathers + reduce-scatter)
+    roof = {"bound": "nvlink", "kernel": "NCCL all-gather of E(l) / G(l) per layer + reduce-scatter of d",
+            "achieved": coll / step_s / 1e9, "peak": 770.0, "unit": "GB/s", "frac": coll / step_s / 1e9 / 770.0,
+            "peak_source": "B200_PROFILING.md measured peer copy, per direction per GPU", "traffic": None,
+            "note": "(2L + 1) x (N-1)/N x n_nodes x D x 4 B received per rank and step / whole-step time; the block SpMMs "
+                    "(1/N of %.1f GB each by the no-reuse bound) run between the collectives" % ((nnz * (8 + 4 * d) + n * 4 * d) / 1e9)}
+    config = {"workload": "configs[3]: LightGCN %dM x %dk, 3 layers, dim=64, nnz(A_hat) = %d, node rows partitioned over %d B200, "
+                          "batch=%d per rank" % (nu // 1_000_000, ni // 1000, nnz, world, b),
+              "n_users": nu, "n_items": ni, "dim": d, "layers": L, "nnz": nnz, "batch_per_gpu": b, "global_batch": b * world,
+              "optimizer": "adam", "lr": 0.05, "keep_pro": 0.6, "dropout_rng": "cuda (same mask on every rank)",
+              "parallelism": "1-D row partition x%d, all-gather per layer" % world}
+    line = _base_line(a, "BPR interactions/sec (LightGCN, whole-graph propagate per batch)", "interactions/s", b * world / step_s, ms,
+                      config, roof, clocks, None, None, {"final_loss": loss, "graph_steps_per_s": 1.0 / step_s})
+    line["n_gpus"] = world
+    line["steps"] = steps
+    return line
+
+
 # --------------------------------------------------------------------------- #
 # config 5: embedding gather / scatter-add / gather+SGD microbench
 # --------------------------------------------------------------------------- #
