@@ -306,10 +306,12 @@ template <int BN>
 int launch_tc(const TcArgs& a, cudaStream_t st) {
     constexpr size_t smem = (size_t)tc_stages(BN) * (2 * TC_M * TC_BK + 2 * BN * TC_BK) * sizeof(float);
     auto k = linear_tc_kernel<BN>;
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[16] = {};  // per device (function attributes are per context) and per BN instantiation
+    int dev = 0;
+    BRS_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 16 || !configured[dev]) {
         BRS_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
+        if (dev >= 0 && dev < 16) configured[dev] = true;
     }
     if ((a.M + TC_M - 1) / TC_M > 65535) return BRS_ERR_UNSUPPORTED;
     dim3 grid(a.N_total / BN, (a.M + TC_M - 1) / TC_M);
