@@ -2,12 +2,14 @@
 
 The reference runs the whole-graph propagate of beta_rec/models/lightgcn.py:46-78 (L sparse products with the
 [N, N] normalised adjacency, N = n_users + n_items) and its backward for EVERY batch; that is the step's cost.
-Here the node rows are partitioned 1-D into N contiguous blocks: rank r owns rows
-[r*blk, (r+1)*blk) of the parameters E0 (+ optimizer state), of A_hat and of A_hat^T, and feeds its own batch.
+Here the node rows are partitioned 1-D: rank r owns the r-th block of the USER rows and
+the r-th block of the ITEM rows (two contiguous ranges; item rows are ~10x denser than user rows, so one contiguous
+range per rank would leave a rank with most of the non-zeros) of the parameters E0 (+ optimizer state), of A_hat
+and of A_hat^T (same pattern, so the backward is balanced too), and feeds its own batch.
 
-  gather    E0 blocks -> every rank holds the full layer-0 matrix                 [NCCL all-gather]
-  forward   per layer: E(l+1)[own rows] = A_hat[own rows, :] E(l)  (brs_spmm_csr, the edge-dropout mask
-            folded in) then all-gather -> full E(l+1)                             [block SpMM + all-gather]
+  gather    E0 blocks -> every rank holds the full layer-0 matrix                 [NCCL all-gather x2: users, items]
+  forward   per layer: E(l+1)[own rows] = A_hat[own rows, :] E(l)  (brs_spmm_csr per range, the edge-dropout mask
+            folded in) then all-gather -> full E(l+1)
   tail      softplus-BPR + L2 on the rank's own batch, scaled for the GLOBAL batch mean (brs_lightgcn_tail):
             loss sum, sparse d = d loss / d E(l) into a full [N, D] buffer
   reduce    d summed over the ranks, each keeps its rows                          [NCCL reduce-scatter]
@@ -52,11 +54,7 @@ class ShardedLightGCNEngine(object):
         self.opt_kind, self.lr = m["optimizer"], float(m["lr"])
         n = self.n_users + self.n_items
         self.n = n
-        self.blk = (n + w - 1) // w          # rows per rank; the last block is padded with empty rows
-        self.n_pad = self.blk * w
-        self.row_lo = self.rank * self.blk
-        self.row_hi = min(n, self.row_lo + self.blk)
-        # ---- adjacency: full CSR arrays on the device, sliced per rank (pattern of A_hat is symmetric: A_hat^T shares it)
+        # ---- adjacency: full CSR arrays on the device (pattern of A_hat is symmetric: A_hat^T shares it)
         adj = m["norm_adj"]
         if hasattr(adj, "csr_tensors"):
             csr = {k: v.to(dev) for k, v in adj.csr_tensors().items()}
@@ -68,15 +66,29 @@ class ShardedLightGCNEngine(object):
             self.nnz = c["nnz"]
             csr = {k: torch.from_numpy(v).to(dev) for k, v in c.items() if k != "nnz"}
         self._csr = csr
-        self._fwd = self._block(csr["row_ptr"], csr["col"], csr["val"], None)
-        self._bwd = self._block(csr["row_ptr_t"], csr["col_t"], csr["val_t"], csr["edge_id_t"])
-        # ---- layer buffers (full, padded), gradient chain buffers, the own block of the parameters
+        # ---- the rank's rows: block r of the user rows and block r of the item rows
+        self.parts = []  # per entity: node offset, rows of the entity, rows per rank, own [lo, hi), offset inside the own block
+        own_off = 0
+        for off, cnt in ((0, self.n_users), (self.n_users, self.n_items)):
+            blk = (cnt + w - 1) // w
+            lo = off + min(cnt, self.rank * blk)
+            hi = off + min(cnt, (self.rank + 1) * blk)
+            part = {"off": off, "cnt": cnt, "blk": blk, "lo": lo, "hi": hi, "own_off": own_off}
+            part["fwd"] = self._block(csr["row_ptr"], csr["col"], csr["val"], None, lo, hi)
+            part["bwd"] = self._block(csr["row_ptr_t"], csr["col_t"], csr["val_t"], csr["edge_id_t"], lo, hi)
+            if cnt != blk * w:  # not divisible: collectives go through a padded staging copy of the entity's rows
+                part["stage"] = torch.zeros((w * blk, self.dim), dtype=torch.float32, device=dev)
+            self.parts.append(part)
+            own_off += blk
+        self.own_rows = own_off
+        # ---- layer buffers (full), gradient chain buffers, the own block of the parameters
         f32 = torch.float32
-        self._layers = [torch.zeros((self.n_pad, self.dim), dtype=f32, device=dev) for _ in range(self.n_layers + 1)]
-        self._d = torch.zeros((self.n_pad, self.dim), dtype=f32, device=dev)
-        self._g = [torch.zeros((self.n_pad, self.dim), dtype=f32, device=dev) for _ in range(2)]
-        self._d_blk = torch.zeros((self.blk, self.dim), dtype=f32, device=dev)
-        self.param = torch.zeros((self.blk, self.dim), dtype=f32, device=dev)  # rows [row_lo, row_lo + blk) of cat(E_user, E_item)
+        self._layers = [torch.zeros((n, self.dim), dtype=f32, device=dev) for _ in range(self.n_layers + 1)]
+        self._d = torch.zeros((n, self.dim), dtype=f32, device=dev)
+        self._g = [torch.zeros((n, self.dim), dtype=f32, device=dev) for _ in range(2)]
+        self._d_blk = torch.zeros((self.own_rows, self.dim), dtype=f32, device=dev)
+        self._tmp_blk = torch.zeros((self.own_rows, self.dim), dtype=f32, device=dev)
+        self.param = torch.zeros((self.own_rows, self.dim), dtype=f32, device=dev)  # [user block | item block], zero padded
         self.grad = torch.zeros_like(self.param)
         if state is None:
             torch.manual_seed(2020)
@@ -88,7 +100,8 @@ class ShardedLightGCNEngine(object):
         else:
             full = torch.from_numpy(np.concatenate([np.asarray(state["user_embedding.weight"], dtype=np.float32),
                                                     np.asarray(state["item_embedding.weight"], dtype=np.float32)]))
-        self.param[: self.row_hi - self.row_lo].copy_(full[self.row_lo:self.row_hi])
+        for pt in self.parts:
+            self.param[pt["own_off"]: pt["own_off"] + pt["hi"] - pt["lo"]].copy_(full[pt["lo"]:pt["hi"]])
         self.opt = RowOptimizer(self.opt_kind, self.lr, "dense")
         self._st = self.opt.add_param("all_embeddings", self.param)
         self._t = 0
@@ -116,22 +129,18 @@ class ShardedLightGCNEngine(object):
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream
 
-    def _block(self, row_ptr, col, val, edge_id):
-        """CSR of the rank's row block: rebased row_ptr (padded with empty rows), views into col / val / edge_id."""
-        lo, hi = self.row_lo, self.row_hi
+    def _block(self, row_ptr, col, val, edge_id, lo, hi):
+        """CSR of the row range [lo, hi): rebased row_ptr, views into col / val / edge_id."""
         rp = row_ptr[lo:hi + 1].to(torch.int64) if hi > lo else torch.zeros(1, dtype=torch.int64, device=self.device)
         first = int(rp[0].item()) if hi > lo else 0
         last = int(rp[-1].item()) if hi > lo else 0
-        local = (rp - first).to(torch.int32)
-        if local.numel() < self.blk + 1:
-            local = torch.cat([local, local[-1:].expand(self.blk + 1 - local.numel())])
-        local = local.contiguous()
+        local = (rp - first).to(torch.int32).contiguous()
         blk = {"row_ptr": local, "col": col[first:last], "val": val[first:last], "first": first, "nnz": last - first,
                "edge_id": None if edge_id is None else edge_id[first:last]}
         blk["struct"] = _lib.Csr(_lib.ptr(local), _lib.ptr(blk["col"]) if last > first else _lib.ptr(col),
                                  _lib.ptr(blk["val"]) if last > first else _lib.ptr(val),
                                  None if edge_id is None else (_lib.ptr(blk["edge_id"]) if last > first else _lib.ptr(edge_id)),
-                                 self.blk, last - first)
+                                 max(hi - lo, 0), last - first)
         return blk
 
     def _spmm(self, blk, mask, x_full, y_blk):
@@ -148,16 +157,39 @@ class ShardedLightGCNEngine(object):
         """LightGCN.dropout's mask (lightgcn.py:32-33) on the device generator: identical on every rank."""
         return (torch.rand(self.nnz, device=self.device, generator=self._gen) + self.keep_prob).int().bool().to(torch.uint8)
 
-    def _own(self, buf):
-        return buf[self.row_lo:self.row_lo + self.blk]
+    def _spmm_own(self, which, mask, x_full, y_own):
+        """y_own[own rows] += (A_hat or A_hat^T)[own rows, :] x_full, one block product per range."""
+        for pt in self.parts:
+            self._spmm(pt[which], mask, x_full, y_own[pt["own_off"]: pt["own_off"] + pt["blk"]])
+
+    def _gather_full(self, dst_full, own):
+        """dst_full [n, D] <- every rank's block (own: [own_rows, D], user part then item part)."""
+        for pt in self.parts:
+            src = own[pt["own_off"]: pt["own_off"] + pt["blk"]]
+            if "stage" in pt:
+                dist.all_gather_into_tensor(pt["stage"], src.contiguous(), group=self.group)
+                dst_full[pt["off"]: pt["off"] + pt["cnt"]].copy_(pt["stage"][: pt["cnt"]])
+            else:
+                dist.all_gather_into_tensor(dst_full[pt["off"]: pt["off"] + pt["cnt"]], src.contiguous(), group=self.group)
+
+    def _reduce_own(self, src_full, out_own):
+        """out_own <- sum over ranks of src_full[own rows]."""
+        for pt in self.parts:
+            dst = out_own[pt["own_off"]: pt["own_off"] + pt["blk"]]
+            if "stage" in pt:
+                pt["stage"][: pt["cnt"]].copy_(src_full[pt["off"]: pt["off"] + pt["cnt"]])
+                pt["stage"][pt["cnt"]:].zero_()
+                dist.reduce_scatter_tensor(dst, pt["stage"], op=dist.ReduceOp.SUM, group=self.group)
+            else:
+                dist.reduce_scatter_tensor(dst, src_full[pt["off"]: pt["off"] + pt["cnt"]], op=dist.ReduceOp.SUM, group=self.group)
 
     def propagate(self, keep_mask):
-        dist.all_gather_into_tensor(self._layers[0], self.param, group=self.group)
+        self._gather_full(self._layers[0], self.param)
         for l in range(self.n_layers):
-            own = self._own(self._layers[l + 1])
+            own = self._tmp_blk
             own.zero_()
-            self._spmm(self._fwd, keep_mask, self._layers[l], own)
-            dist.all_gather_into_tensor(self._layers[l + 1], own.clone(), group=self.group)
+            self._spmm_own("fwd", keep_mask, self._layers[l], own)
+            self._gather_full(self._layers[l + 1], own)
 
     def train_single_batch(self, batch_data, keep_mask=None):
         """LightGCNEngine.train_single_batch (lightgcn.py:119-152) on this rank's batch; returns the GLOBAL batch loss."""
@@ -181,28 +213,32 @@ class ShardedLightGCNEngine(object):
         self.propagate(keep_mask)
         # ---- tail on the own batch (mean over the global batch); d summed over ranks, own rows kept
         _lib.check(lib.brs_lightgcn_tail(self._cmodel, _lib.ptr(users), _lib.ptr(pos), _lib.ptr(neg), b, gb, st()), "brs_lightgcn_tail")
-        dist.reduce_scatter_tensor(self._d_blk, self._d, op=dist.ReduceOp.SUM, group=self.group)
+        self._reduce_own(self._d, self._d_blk)
         # ---- backward of the propagate: G(L) = d, G(l) = d + A_hat^T G(l+1)
         ci = 1
-        dist.all_gather_into_tensor(self._g[ci], self._d_blk, group=self.group)
+        self._gather_full(self._g[ci], self._d_blk)
         for l in range(self.n_layers - 1, -1, -1):
             if l == 0:
                 self.grad.copy_(self._d_blk)
-                self._spmm(self._bwd, keep_mask, self._g[ci], self.grad)
+                self._spmm_own("bwd", keep_mask, self._g[ci], self.grad)
             else:
-                own = self._d_blk.clone()
-                self._spmm(self._bwd, keep_mask, self._g[ci], own)
-                dist.all_gather_into_tensor(self._g[1 - ci], own, group=self.group)
+                own = self._tmp_blk
+                own.copy_(self._d_blk)
+                self._spmm_own("bwd", keep_mask, self._g[ci], own)
+                self._gather_full(self._g[1 - ci], own)
                 ci = 1 - ci
         # ---- L2 term on the layer-0 rows of EVERY rank's batch that fall into the own rows
         mine = torch.stack([users, pos, neg])
         everyone = torch.empty((self.world,) + tuple(mine.shape), dtype=torch.int64, device=dev)
         dist.all_gather_into_tensor(everyone, mine, group=self.group)
-        if self.row_hi > self.row_lo:
+        for pt in self.parts:
+            if pt["hi"] <= pt["lo"]:
+                continue
+            gpart = self.grad[pt["own_off"]:]
             for r in range(self.world):
                 u, p, q = everyone[r]
-                _lib.check(lib.brs_lightgcn_reg_grad(self._cmodel, _lib.ptr(u), _lib.ptr(p), _lib.ptr(q), b, gb, self.row_lo,
-                                                     self.row_hi, _lib.ptr(self.grad), st()), "brs_lightgcn_reg_grad")
+                _lib.check(lib.brs_lightgcn_reg_grad(self._cmodel, _lib.ptr(u), _lib.ptr(p), _lib.ptr(q), b, gb, pt["lo"], pt["hi"],
+                                                     _lib.ptr(gpart), st()), "brs_lightgcn_reg_grad")
         # ---- optimizer on the own rows, loss over the global batch
         self._t += 1
         _lib.check(lib.brs_dense_params_step(self._dense, 1, self.opt.desc, self._t, st()), "brs_dense_params_step")
@@ -213,7 +249,7 @@ class ShardedLightGCNEngine(object):
 
     def gather_state(self):
         """{"user_embedding.weight", "item_embedding.weight"} (numpy), identical on every rank."""
-        full = torch.empty((self.n_pad, self.dim), dtype=torch.float32, device=self.device)
-        dist.all_gather_into_tensor(full, self.param, group=self.group)
-        full = full[: self.n].cpu().numpy()
+        full = torch.empty((self.n, self.dim), dtype=torch.float32, device=self.device)
+        self._gather_full(full, self.param)
+        full = full.cpu().numpy()
         return {"user_embedding.weight": full[: self.n_users].copy(), "item_embedding.weight": full[self.n_users:].copy()}
