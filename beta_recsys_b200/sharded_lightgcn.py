@@ -31,6 +31,20 @@ from .engines.lightgcn import coo_to_csr
 from .engines.torch_engine import RowOptimizer
 
 
+def partition_rows(n_users, n_items, world, rank):
+    """Host-side index rule (pure; covered by the CPU tests): the node rows rank `rank` owns -- block `rank` of the
+    user rows and block `rank` of the item rows -- as a list of dicts {off, cnt, blk, lo, hi, own_off}: node offset
+    and size of the entity, rows per rank (ceil), the own node range [lo, hi) and its offset inside the rank's own
+    block (user part, then item part, each padded to blk rows)."""
+    parts, own_off = [], 0
+    for off, cnt in ((0, int(n_users)), (int(n_users), int(n_items))):
+        blk = (cnt + world - 1) // world
+        parts.append({"off": off, "cnt": cnt, "blk": blk, "lo": off + min(cnt, rank * blk), "hi": off + min(cnt, (rank + 1) * blk),
+                      "own_off": own_off})
+        own_off += blk
+    return parts, own_off
+
+
 class ShardedLightGCNEngine(object):
     def __init__(self, config, group=None, state=None):
         """config["model"]: the reference's LightGCN keys (lightgcn.py:104-117) with ``norm_adj`` either the reference's
@@ -67,20 +81,12 @@ class ShardedLightGCNEngine(object):
             csr = {k: torch.from_numpy(v).to(dev) for k, v in c.items() if k != "nnz"}
         self._csr = csr
         # ---- the rank's rows: block r of the user rows and block r of the item rows
-        self.parts = []  # per entity: node offset, rows of the entity, rows per rank, own [lo, hi), offset inside the own block
-        own_off = 0
-        for off, cnt in ((0, self.n_users), (self.n_users, self.n_items)):
-            blk = (cnt + w - 1) // w
-            lo = off + min(cnt, self.rank * blk)
-            hi = off + min(cnt, (self.rank + 1) * blk)
-            part = {"off": off, "cnt": cnt, "blk": blk, "lo": lo, "hi": hi, "own_off": own_off}
-            part["fwd"] = self._block(csr["row_ptr"], csr["col"], csr["val"], None, lo, hi)
-            part["bwd"] = self._block(csr["row_ptr_t"], csr["col_t"], csr["val_t"], csr["edge_id_t"], lo, hi)
-            if cnt != blk * w:  # not divisible: collectives go through a padded staging copy of the entity's rows
-                part["stage"] = torch.zeros((w * blk, self.dim), dtype=torch.float32, device=dev)
-            self.parts.append(part)
-            own_off += blk
-        self.own_rows = own_off
+        self.parts, self.own_rows = partition_rows(self.n_users, self.n_items, w, self.rank)
+        for part in self.parts:
+            part["fwd"] = self._block(csr["row_ptr"], csr["col"], csr["val"], None, part["lo"], part["hi"])
+            part["bwd"] = self._block(csr["row_ptr_t"], csr["col_t"], csr["val_t"], csr["edge_id_t"], part["lo"], part["hi"])
+            if part["cnt"] != part["blk"] * w:  # not divisible: collectives go through a padded staging copy of the entity's rows
+                part["stage"] = torch.zeros((w * part["blk"], self.dim), dtype=torch.float32, device=dev)
         # ---- layer buffers (full), gradient chain buffers, the own block of the parameters
         f32 = torch.float32
         self._layers = [torch.zeros((n, self.dim), dtype=f32, device=dev) for _ in range(self.n_layers + 1)]

@@ -35,6 +35,16 @@ _TABLES = (("user", "embedding_user_mlp.weight", "mlp"), ("user", "embedding_use
            ("item", "embedding_item_mlp.weight", "mlp"), ("item", "embedding_item_mf.weight", "mf"))
 
 
+def bucket_by_owner(ids, world):
+    """Host-side index rule of the exchange (pure; covered by the CPU tests): the permutation that sorts a batch's
+    ids by owner = id mod world (stable), the number of ids per owner, and the owners' local row numbers in that
+    order.  Works on CPU and CUDA tensors."""
+    owner = ids % world
+    order = torch.argsort(owner, stable=True)
+    counts = torch.bincount(owner, minlength=world)
+    return order, counts, (ids // world)[order].contiguous()
+
+
 class ShardedNeuMFEngine(object):
     def __init__(self, config, group=None, state=None):
         """config["model"]: the reference's NeuMF keys (ncf.py:82-98) + adam_mode; ``state``: a full (unsharded)
@@ -99,11 +109,9 @@ class ShardedNeuMFEngine(object):
     def _route(self, ids):
         """Bucket the batch's ids by owner and send each owner its local row numbers.  Returns (order, send_counts,
         recv_counts, recv_local_rows): ``order`` sorts the batch by owner (stable)."""
-        owner = ids % self.world
-        order = torch.argsort(owner, stable=True)
-        counts = torch.bincount(owner, minlength=self.world)
+        order, counts, local = bucket_by_owner(ids, self.world)
         send_counts = counts.tolist()
-        recv, recv_counts = all_to_all_v((ids // self.world)[order].contiguous(), send_counts, self.group)
+        recv, recv_counts = all_to_all_v(local, send_counts, self.group)
         return order, send_counts, recv_counts, recv
 
     def _exchange(self, send, in_counts, out_counts):

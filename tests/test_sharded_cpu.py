@@ -103,3 +103,70 @@ def test_triple_routing_exchange_gloo_world2():
     for p in procs:
         p.join(timeout=30)
     assert sorted(res) == [(0, "ok"), (1, "ok")], res
+
+
+# --------------------------------------------------------------------------- #
+# host-side index rules of the sharded NeuMF / LightGCN engines
+# --------------------------------------------------------------------------- #
+def test_lightgcn_row_partition_covers_every_node_once():
+    from beta_recsys_b200.sharded_lightgcn import partition_rows
+
+    for nu, ni, world in ((1501, 733, 2), (1_000_000, 100_000, 8), (7, 3, 4), (10, 10, 1)):
+        seen = np.zeros(nu + ni, dtype=np.int64)
+        for rank in range(world):
+            parts, own_rows = partition_rows(nu, ni, world, rank)
+            assert own_rows == sum(p["blk"] for p in parts)
+            assert [p["own_off"] for p in parts] == [0, parts[0]["blk"]]
+            for p in parts:
+                assert p["off"] <= p["lo"] <= p["hi"] <= p["off"] + p["cnt"] and p["hi"] - p["lo"] <= p["blk"]
+                seen[p["lo"]:p["hi"]] += 1
+        assert (seen == 1).all()  # every user and item row has exactly one owner
+
+
+def _neumf_route_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from beta_recsys_b200 import sharded
+        from beta_recsys_b200.sharded_ncf import bucket_by_owner
+
+        rng = np.random.default_rng(50 + rank)
+        ids = torch.from_numpy(rng.integers(0, 1000, 257))
+        order, counts, local = bucket_by_owner(ids, world)
+        assert sorted(order.tolist()) == list(range(257)) and int(counts.sum()) == 257
+        assert torch.equal((ids % world)[order], torch.sort(ids % world, stable=True).values)
+        # owners receive local row numbers; serving rows and sending them back restores the batch order
+        recv, rc = sharded.all_to_all_v(local, counts.tolist())
+        table = torch.arange(1000 // world + 1, dtype=torch.float32).view(-1, 1) * world + rank  # local row r holds its global id
+        served = table[recv]
+        back, _ = sharded.all_to_all_v(served, rc)
+        got = torch.empty(257, 1)
+        got.index_copy_(0, order, back)
+        assert torch.equal(got.view(-1).long(), ids)
+        q.put((rank, "ok"))
+    except Exception as e:  # pragma: no cover
+        q.put((rank, repr(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(400)
+def test_neumf_row_exchange_gloo_world2():
+    world, port = 2, _free_port()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    os.environ["PYTHONPATH"] = root + os.pathsep + os.environ.get("PYTHONPATH", "")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_neumf_route_worker, args=(r, world, port, q)) for r in range(world)]
+    saved = sys.path[:]
+    sys.path[:] = [root] + [x for x in saved if x != root]
+    try:
+        for p in procs:
+            p.start()
+    finally:
+        sys.path[:] = saved
+    res = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=30)
+    assert sorted(res) == [(0, "ok"), (1, "ok")], res
