@@ -374,12 +374,15 @@ def sharded_parity(a, rank, world, local, dev):
                 ol, orr = O.mf_train_single_batch(p, st, g, "bpr", optimizer, lr, 0.0)
                 worst_loss = max(worst_loss, abs(loss - ol) / max(1.0, abs(ol)), abs(reg - orr) / max(1.0, abs(orr)))
                 got = eng.gather_state()
-                for k in p:  # this step's UPDATE against the oracle's, relative to max|dw| (+ 2 ulp of the fp32 parameter)
+                for k in p:  # this step's UPDATE against the oracle's, relative to max|dw| (+ (world + 1) ulp of the parameter)
                     if k == "global_bias":
                         continue  # sums 2B opposite-sign terms: covered by the bit-identity check below and the loss
                     dw = p[k].astype(np.float64) - before[k]
                     dg = got[k].astype(np.float64) - before[k]
-                    ulp = 2.0 * np.spacing(np.maximum(np.abs(p[k]), np.abs(before[k])).astype(np.float32)).astype(np.float64)
+                    # the SGD push adds every rank's -lr*g partial straight into the owner's fp32 weight: one rounding
+                    # per contributing rank where the oracle rounds once (measured at N = 8 with a 2-ulp allowance:
+                    # 1.75e-3 of max|dw| on the bias tables, identical in both shard modes, i.e. deterministic rounding)
+                    ulp = (world + 1.0) * np.spacing(np.maximum(np.abs(p[k]), np.abs(before[k])).astype(np.float32)).astype(np.float64)
                     err = np.maximum(np.abs(dg - dw) - ulp, 0.0).max() / max(np.abs(dw).max(), 1e-30)
                     if optimizer == "adam":  # lr*m/(sqrt(v)+eps) is ill-conditioned in fp32 where g ~ eps: bound by lr
                         err = np.abs(dg - dw).max() / lr
@@ -401,7 +404,8 @@ def sharded_parity(a, rank, world, local, dev):
     out["pass"] = bool(out["max_rel_dw"] <= 1e-4 and out["max_rel_loss"] <= 1e-5 and adam_err <= 2e-3 and
                        out["global_bias_bit_identical"])
     out["what"] = ("5003 x 1999 x dim %d, batch %d per rank, %d ranks: sharded engines (each rank its own batch) vs the numpy "
-                   "oracle on the concatenated global batch; SGD updates relative to max|dw| (tolerance 1e-4 + 2 ulp), losses "
+                   "oracle on the concatenated global batch; SGD updates relative to max|dw| (tolerance 1e-4 + (world + 1) ulp: the push "
+                   "rounds once per contributing rank), losses "
                    "1e-5, dense-Adam first step |dw| error / lr" % (d, bsz, world))
     flag = torch.tensor([1.0 if out["pass"] else 0.0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
