@@ -413,6 +413,52 @@ def sharded_parity(a, rank, world, local, dev):
     return out
 
 
+def single_gpu_same_tables(a, dev, steps=200):
+    """The one-GPU step (MFEngine, row-owner kernels) on the SAME table size as the sharded run, measured on rank 0
+    before the sharded engine is built: the apples-to-apples denominator for the scaling ratio (the N = 1 bench line
+    itself is BASELINE's configs[1] at 1M x 100k).  Never fatal: any failure is reported in the field."""
+    import io
+    from contextlib import redirect_stdout
+
+    try:
+        from beta_recsys_b200 import _lib
+        from beta_recsys_b200.engines import MFEngine
+
+        lib = _lib.load()
+        cfg = {"model": dict(device_str=str(dev), n_users=a.users, n_items=a.items, emb_dim=a.dim, batch_size=a.batch,
+                             optimizer=a.optimizer, lr=0.05, loss="bpr", adam_mode=a.adam_mode),
+               "system": {"run_dir": "/tmp/brs_bench"}}
+        with redirect_stdout(io.StringIO()):
+            eng = MFEngine(cfg)
+        nb = 64
+        users, pos, neg = make_batches(a.users, a.items, a.batch, nb, SEED, dev)
+        out = torch.empty((nb, 4), dtype=torch.float32, device=dev)
+        stream = torch.cuda.current_stream(dev)
+
+        def run():
+            _lib.check(lib.brs_mf_train_batches(eng._cmodel, eng.optimizer.desc, 0, _lib.ptr(users), _lib.ptr(pos), _lib.ptr(neg),
+                                                nb * a.batch, a.batch, 0.0, _lib.ptr(out), stream.cuda_stream), "train_batches")
+
+        run()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = max(1, steps // nb)
+        e0.record(stream)
+        for _ in range(reps):
+            run()
+        e1.record(stream)
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / (reps * nb)
+        res = {"value": a.batch / (ms * 1e-3), "unit": "interactions/s", "ms_per_step": ms, "steps": reps * nb,
+               "what": "MFEngine (one GPU, row-owner step) on the same %d x %d tables, same batch, device-resident batches"
+                       % (a.users, a.items)}
+        del eng, users, pos, neg, out
+        torch.cuda.empty_cache()
+        return res
+    except Exception as ex:  # pragma: no cover
+        return {"error": repr(ex)[:200]}
+
+
 def run_sharded(a, rank, world, local, dev):
     """N > 1: tables row-sharded over the ranks (owner = row mod N), per-rank batch fixed (weak scaling).
     Rows travel over NVLink peer memory inside the fused kernel; two flag barriers per step."""
@@ -421,6 +467,8 @@ def run_sharded(a, rank, world, local, dev):
     from beta_recsys_b200.sharded import ShardedMFEngine
 
     parity = None if a.no_parity or a.profile else sharded_parity(a, rank, world, local, dev)
+    one_gpu = single_gpu_same_tables(a, dev) if (rank == 0 and not a.profile) else None
+    dist.barrier()
     cfg = {"model": dict(device_str="cuda:%d" % local, n_users=a.users, n_items=a.items, emb_dim=a.dim,
                          batch_size=a.batch, optimizer=a.optimizer, lr=0.05, loss="bpr", adam_mode=a.adam_mode)}
     eng = ShardedMFEngine(cfg, route=a.route)
@@ -548,7 +596,10 @@ def run_sharded(a, rank, world, local, dev):
             # pre-pass, [pull,] fused fwd/bwd, barrier, push, count reset, apply/record, barrier
             "gpu_launches": (8 if os.environ.get("BRS_SHARD_MODE", "2" if world >= 8 else "1") == "2" else 7) * a.steps,
             "final_loss": final_loss, "wall_s_timed_region": t_wall1 - t_wall0, "parity": parity,
+            "single_gpu_same_tables": one_gpu,
         }
+        if one_gpu and "value" in one_gpu:
+            line["speedup_vs_single_gpu_same_tables"] = value / one_gpu["value"]
         print(json.dumps(line))
     dist.destroy_process_group()
 
