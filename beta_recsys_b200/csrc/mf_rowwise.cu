@@ -482,11 +482,11 @@ __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg((const flo
 
 // users kernel: ONE WARP PER WORK UNIT of the user stream, everything in registers (the only shared memory
 // is the unit's record tile); rows are gathered with plain 128-bit read-only loads -- one warp instruction
-// per 512-byte row at dim 128, up to 12 in flight per warp, ~20 warps per SM -- so the Zipf-hot rows hit L1
+// per 512-byte row at dim 128, 12 in flight per warp, ~20 warps per SM -- so the Zipf-hot rows hit L1
 // and nothing has to be staged.  Per block of 4 samples:
-//   load     pos / neg item rows (+ the user row at the first sample of a row part), the three biases on
-//            lanes 0..2
-//   phase 1  per-lane partial dots u.i, u.j (+ the bias a lane loaded)
+//   load     user, pos-item and neg-item rows of every sample (consecutive samples of a user hit L1); the three
+//            biases of sample k by the 8 lanes that later run sample k's loss chain
+//   phase 1  per-lane partial dots u.i, u.j
 //   phase 2  ONE transposing reduction for the block's 8 dots, then the sigmoid / loss / d loss chain once
 //            per block (lanes 8k .. 8k+7 work on sample k); (coefficient, user slot) -> item stream
 //   phase 3  gradient of the user row accumulated in registers; at the end of a row part: regularizer term
