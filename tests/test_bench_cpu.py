@@ -32,3 +32,20 @@ def test_reference_arm_other_ranks_exit_quietly():
     out = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600, env=env)
     assert out.returncode == 0, out.stderr[-2000:]
     assert not [l for l in out.stdout.splitlines() if l.startswith("{")]
+
+
+def test_reference_arm_of_the_other_configs_prints_a_contract_line():
+    """--config 3 / 4 / 5 have their own CPU arms (bench_configs.cpu_*): same line contract, their own metric."""
+    for config, metric, extra in ((5, "embedding gather HBM GB/s (D=128)", ["--rows", "200000"]),
+                                  (4, "BPR interactions/sec (LightGCN, whole-graph propagate per batch)",
+                                   ["--users", "3000", "--items", "700", "--edges", "20000", "--batch", "512"])):
+        cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--config", str(config), "--steps", "3",
+               "--warmup", "1"] + extra
+        out = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=900)
+        assert out.returncode == 0, out.stderr[-2000:]
+        lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+        assert len(lines) == 1
+        d = json.loads(lines[0])
+        assert d["impl"] == "reference" and d["metric"] == metric and d["value"] > 0 and d["gpu_launches"] == 0
+        assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"]
+        assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["unit"] == d["unit"]
