@@ -938,6 +938,9 @@ extern "C" int brs_mf_plan_build(const brs_mf_model* model, int32_t which, int32
         const long long cap = (long long)brs_sm_count() * 4;
         if (blocks > cap) blocks = cap;
         mf_plan_claim_kernel<<<(int)blocks, kPlanThreads, 0, st>>>(a);
+    } else {
+        // the claim kernel is what resets the stream cursors: an empty batch must not inherit the previous plan's
+        BRS_CUDA_CHECK(cudaMemsetAsync(a.pv.hdr, 0, 2 * sizeof(int), st));
     }
     {
         const int cmax = pl.user_capacity > pl.item_capacity ? pl.user_capacity : pl.item_capacity;
